@@ -1,0 +1,981 @@
+// C ABI of libescb200 (include/escb200.h): handle, checkpoint tensors, weight packing and the
+// encode / decode / forward drivers that sequence the kernels of swin.cu / pvq.cu / frontend.cu.
+//
+// Reference control flow restated here (paths under the reference root):
+//   ESC.encode / decode / forward ............ esc/models/codecs.py:30-94
+//   Encoder.forward .......................... esc/models/base.py:143-158
+//   CrossScaleRVQDecoder.encode/decode/forward esc/models/csrvq.py:97-182
+//   TransformerLayer.forward ................. esc/modules/transformer/attention.py:48-91
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "internal.h"
+
+namespace escb {
+bool attention_supported(int hd);
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+struct Weight {
+    std::string name;
+    std::vector<int64_t> shape;
+    int64_t numel = 1;
+    std::vector<float> host;
+    bool set = false;
+};
+
+struct Level { int C, H; };   // H = frequency patches at this scale
+
+}  // namespace escb
+
+using namespace escb;
+
+struct escb_handle {
+    escb_config cfg;
+    int device = 0;
+    int L = 0;                 // levels == streams
+    int F = 0, n_fft = 0, win = 0, hop = 0, pf = 0, pt = 0, C0 = 0, nov = 0;
+    Level lev[ESCB_MAX_LEVELS];
+    std::vector<Weight> weights;
+    std::unordered_map<std::string, int> index;
+    bool finalized = false;
+    float* arena = nullptr;
+    LayerW layers[2 * ESCB_MAX_LEVELS];
+    QuantW quants[ESCB_MAX_LEVELS];
+    FrontW front;
+    std::atomic<long long> launches{0};
+    // grow-only scratch for the *_host entry points
+    std::mutex host_mu;
+    void* host_scratch = nullptr;
+    size_t host_scratch_bytes = 0;
+};
+
+namespace escb {
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t align_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------ manifest
+static void add_weight(escb_handle* h, const std::string& name, std::vector<int64_t> shape) {
+    Weight w;
+    w.name = name;
+    w.shape = shape;
+    for (int64_t s : shape) w.numel *= s;
+    h->index[name] = (int)h->weights.size();
+    h->weights.push_back(std::move(w));
+}
+
+static void add_swin_layer(escb_handle* h, const std::string& p, int C, int heads, int depth, int scale, int out_dim) {
+    const int hidden = C * h->cfg.mlp_hidden_mult;
+    for (int j = 0; j < depth; ++j) {
+        const std::string b = p + ".swint_blocks." + std::to_string(j);
+        add_weight(h, b + ".norm1.weight", {C});
+        add_weight(h, b + ".norm1.bias", {C});
+        add_weight(h, b + ".attn.relative_position_bias_table", {49, heads});
+        add_weight(h, b + ".attn.qkv.weight", {3 * C, C});
+        add_weight(h, b + ".attn.qkv.bias", {3 * C});
+        add_weight(h, b + ".attn.proj.weight", {C, C});
+        add_weight(h, b + ".attn.proj.bias", {C});
+        add_weight(h, b + ".norm2.weight", {C});
+        add_weight(h, b + ".norm2.bias", {C});
+        add_weight(h, b + ".mlp.linear_1.weight", {hidden, C});
+        add_weight(h, b + ".mlp.linear_1.bias", {hidden});
+        add_weight(h, b + ".mlp.linear_2.weight", {C, hidden});
+        add_weight(h, b + ".mlp.linear_2.bias", {C});
+    }
+    if (scale == 1) {
+        add_weight(h, p + ".subsample.norm.weight", {2 * C});
+        add_weight(h, p + ".subsample.norm.bias", {2 * C});
+        add_weight(h, p + ".subsample.down.weight", {out_dim, 2 * C});
+    } else if (scale == 2) {
+        add_weight(h, p + ".subsample.norm.weight", {C});
+        add_weight(h, p + ".subsample.norm.bias", {C});
+        add_weight(h, p + ".subsample.up.weight", {2 * out_dim, C});
+    }
+}
+
+struct LayerDesc { std::string prefix; int C, heads, scale, out_dim, H; };
+
+// layer_index convention of escb_swin_layer: 0 pre_nn, 1..L-1 encoder.blocks, L..2L-2 decoder.blocks, 2L-1 post_nn
+static LayerDesc layer_desc(const escb_handle* h, int li) {
+    const int L = h->L;
+    const escb_config& c = h->cfg;
+    if (li == 0) return {"encoder.pre_nn", c.h_dims[0], c.swin_heads[0], 0, c.h_dims[0], h->lev[0].H};
+    if (li < L) {
+        const int i = li - 1;
+        return {"encoder.blocks." + std::to_string(i), c.h_dims[i], c.swin_heads[i], 1, c.h_dims[i + 1], h->lev[i].H};
+    }
+    if (li < 2 * L - 1) {
+        const int i = li - L;                  // decoder block i works at level L-1-i
+        const int lv = L - 1 - i;
+        return {"decoder.blocks." + std::to_string(i), c.h_dims[lv], c.swin_heads[L - 2 - i], 2, c.h_dims[lv - 1],
+                h->lev[lv].H};
+    }
+    return {"decoder.post_nn", c.h_dims[0], c.swin_heads[0], 0, c.h_dims[0], h->lev[0].H};
+}
+
+struct QuantDesc { int in_dim, in_freq, d, level; };
+static QuantDesc quant_desc(const escb_handle* h, int q) {
+    const int L = h->L;
+    const int lv = q == 0 ? L - 1 : L - q;        // base.py:55-68
+    return {h->cfg.h_dims[lv], h->lev[lv].H, h->cfg.codebook_dims[q], lv};
+}
+
+static void split_dims(int total, int parts, int* out) {   // quantization.py:380-386
+    const int base = total / parts;
+    for (int i = 0; i < parts; ++i) out[i] = base;
+    out[parts - 1] = total - base * (parts - 1);
+}
+
+static void build_manifest(escb_handle* h) {
+    const escb_config& c = h->cfg;
+    for (int q = 0; q < h->L; ++q) {
+        const QuantDesc d = quant_desc(h, q);
+        int vq[3];
+        split_dims(d.in_dim * d.in_freq * c.overlap, 3, vq);
+        const std::string p = "quantizers." + std::to_string(q);
+        for (int g = 0; g < 3; ++g) add_weight(h, p + ".vqs." + std::to_string(g) + ".embedding.weight", {c.codebook_size, d.d});
+        for (int g = 0; g < 3; ++g) add_weight(h, p + ".down_projs." + std::to_string(g) + ".weight", {d.d, vq[g]});
+        for (int g = 0; g < 3; ++g) add_weight(h, p + ".up_projs." + std::to_string(g) + ".weight", {vq[g], d.d});
+    }
+    add_weight(h, "encoder.patch_embed.proj.weight", {h->C0, 2, h->pf, h->pt});
+    add_weight(h, "encoder.patch_embed.proj.bias", {h->C0});
+    add_weight(h, "encoder.patch_embed.norm.weight", {h->C0});
+    add_weight(h, "encoder.patch_embed.norm.bias", {h->C0});
+    for (int li = 0; li < 2 * h->L; ++li) {
+        const LayerDesc d = layer_desc(h, li);
+        add_swin_layer(h, d.prefix, d.C, d.heads, c.swin_depth, d.scale, d.out_dim);
+    }
+    const int n1 = h->C0 * h->pf * h->pt;
+    add_weight(h, "decoder.patch_deembed.de_proj1.weight", {n1, h->C0, 5, 5});
+    add_weight(h, "decoder.patch_deembed.de_proj1.bias", {n1});
+    add_weight(h, "decoder.patch_deembed.de_proj2.weight", {2, h->C0, 3, 3});
+    add_weight(h, "decoder.patch_deembed.de_proj2.bias", {2});
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+struct Arena {
+    std::vector<float> data;
+    size_t push(const std::vector<float>& v) {
+        const size_t off = align_up(data.size(), 32);
+        data.resize(off + v.size(), 0.f);
+        if (!v.empty()) memcpy(data.data() + off, v.data(), v.size() * sizeof(float));
+        return off;
+    }
+};
+
+struct Fix { const float** slot; size_t off; };
+
+struct Packer {
+    escb_handle* h;
+    Arena arena;
+    std::vector<Fix> fixes;
+    const std::vector<float>& w(const std::string& name) const { return h->weights[h->index.at(name)].host; }
+    void put(const float** slot, const std::vector<float>& v) { fixes.push_back({slot, arena.push(v)}); }
+    void put_ln(LnW& ln, const std::string& p, int C) {
+        std::vector<float> g(round_up(C, 4), 0.f), b(round_up(C, 4), 0.f);
+        memcpy(g.data(), w(p + ".weight").data(), C * sizeof(float));
+        memcpy(b.data(), w(p + ".bias").data(), C * sizeof(float));
+        put(&ln.g, g);
+        put(&ln.b, b);
+    }
+    // Wt[k][n] = W[n][k] for a reference nn.Linear weight W [N][K]
+    void put_linear(GemmWeight& gw, const std::string& wname, const char* bname) {
+        const Weight& W = h->weights[h->index.at(wname)];
+        const int N = (int)W.shape[0], K = (int)W.shape[1];
+        std::vector<float> t;
+        init_gemm(gw, N, K, t);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W.host[(size_t)n * K + k];
+        put(&gw.wt, t);
+        gw.bias = nullptr;
+        if (bname) put(&gw.bias, w(bname));
+    }
+    static void init_gemm(GemmWeight& gw, int N, int K, std::vector<float>& t) {
+        gw.N = N;
+        gw.K = K;
+        gw.Kpad = round_up(K, kBK);
+        gw.ldw = round_up(N, 4);
+        gw.bias = nullptr;
+        t.assign((size_t)gw.Kpad * gw.ldw, 0.f);
+    }
+};
+
+static void pack_layer(Packer& P, int li) {
+    escb_handle* h = P.h;
+    const LayerDesc d = layer_desc(h, li);
+    LayerW& lw = h->layers[li];
+    lw.C = d.C;
+    lw.heads = d.heads;
+    lw.hd = d.C / d.heads;
+    lw.depth = h->cfg.swin_depth;
+    lw.scale = d.scale;
+    lw.out_dim = d.out_dim;
+    for (int j = 0; j < lw.depth; ++j) {
+        const std::string b = d.prefix + ".swint_blocks." + std::to_string(j);
+        BlockW& bw = lw.blk[j];
+        P.put_ln(bw.n1, b + ".norm1", d.C);
+        P.put_ln(bw.n2, b + ".norm2", d.C);
+        P.put_linear(bw.qkv, b + ".attn.qkv.weight", (b + ".attn.qkv.bias").c_str());
+        P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str());
+        P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str());
+        P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str());
+        // relative-position bias gathered to [heads][16][16] (attention.py:190-205, 229-232)
+        const std::vector<float>& table = P.w(b + ".attn.relative_position_bias_table");
+        std::vector<float> rb((size_t)d.heads * 256);
+        for (int hh = 0; hh < d.heads; ++hh)
+            for (int i = 0; i < 16; ++i)
+                for (int j2 = 0; j2 < 16; ++j2) {
+                    const int idx = (i / 4 - j2 / 4 + 3) * 7 + (i % 4 - j2 % 4 + 3);
+                    rb[((size_t)hh * 16 + i) * 16 + j2] = table[(size_t)idx * d.heads + hh];
+                }
+        P.put(&bw.relbias, rb);
+    }
+    if (d.scale == 1) {
+        P.put_ln(lw.sn, d.prefix + ".subsample.norm", 2 * d.C);
+        P.put_linear(lw.sub, d.prefix + ".subsample.down.weight", nullptr);
+    } else if (d.scale == 2) {
+        P.put_ln(lw.sn, d.prefix + ".subsample.norm", d.C);
+        P.put_linear(lw.sub, d.prefix + ".subsample.up.weight", nullptr);
+    }
+}
+
+static void pack_quant(Packer& P, int q) {
+    escb_handle* h = P.h;
+    const QuantDesc d = quant_desc(h, q);
+    QuantW& qw = h->quants[q];
+    const int C = d.in_dim, Hq = d.in_freq, dd = d.d, K = h->cfg.codebook_size;
+    const int frame = 2 * C * Hq;
+    int vq[3], start[3];
+    split_dims(frame, 3, vq);
+    start[0] = 0; start[1] = vq[0]; start[2] = vq[0] + vq[1];
+    qw.in_dim = C; qw.in_freq = Hq; qw.d = dd; qw.frame_dim = frame; qw.ncodes = K;
+    const std::string p = "quantizers." + std::to_string(q);
+    std::vector<float> down, up;
+    Packer::init_gemm(qw.down, 3 * dd, frame, down);
+    Packer::init_gemm(qw.up, frame, 3 * dd, up);
+    // reference frame index kref = o*(C*Hq) + c*Hq + h (quantization.py:400-409); ours k' = h*(2C) + o*C + c
+    for (int hh = 0; hh < Hq; ++hh)
+        for (int o = 0; o < 2; ++o)
+            for (int c = 0; c < C; ++c) {
+                const int kref = o * (C * Hq) + c * Hq + hh;
+                const int kp = hh * 2 * C + o * C + c;
+                const int g = kref >= start[2] ? 2 : (kref >= start[1] ? 1 : 0);
+                const int kl = kref - start[g];
+                const std::vector<float>& dw = P.w(p + ".down_projs." + std::to_string(g) + ".weight");   // [d][vq_g]
+                const std::vector<float>& uw = P.w(p + ".up_projs." + std::to_string(g) + ".weight");     // [vq_g][d]
+                for (int j = 0; j < dd; ++j) {
+                    down[(size_t)kp * qw.down.ldw + g * dd + j] = dw[(size_t)j * vq[g] + kl];
+                    up[(size_t)(g * dd + j) * qw.up.ldw + kp] = uw[(size_t)kl * dd + j];
+                }
+            }
+    P.put(&qw.down.wt, down);
+    P.put(&qw.up.wt, up);
+    // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
+    std::vector<float> raw((size_t)3 * K * dd), cbn((size_t)3 * K * dd), cn((size_t)3 * K);
+    for (int g = 0; g < 3; ++g) {
+        const std::vector<float>& e = P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight");
+        for (int c = 0; c < K; ++c) {
+            float ss = 0.f;
+            for (int j = 0; j < dd; ++j) { const float v = e[(size_t)c * dd + j]; ss = fmaf(v, v, ss); }
+            const float den = fmaxf(sqrtf(ss), 1e-12f);
+            float s2 = 0.f;
+            for (int j = 0; j < dd; ++j) {
+                const float v = e[(size_t)c * dd + j];
+                const float nv = v / den;
+                raw[((size_t)g * K + c) * dd + j] = v;
+                cbn[((size_t)g * K + c) * dd + j] = nv;
+                s2 = fmaf(nv, nv, s2);
+            }
+            cn[(size_t)g * K + c] = s2;
+        }
+    }
+    P.put(&qw.raw, raw);
+    P.put(&qw.cbn, cbn);
+    P.put(&qw.cnorm, cn);
+}
+
+static void pack_front(Packer& P) {
+    escb_handle* h = P.h;
+    FrontW& f = h->front;
+    const int F = h->F, N = h->n_fft, win = h->win, hop = h->hop, C0 = h->C0;
+    const int padl = (N - win) / 2;
+    f.F = F; f.win = win; f.hop = hop; f.nov = h->nov; f.C0 = C0; f.pf = h->pf; f.pt = h->pt;
+    const double PI = 3.14159265358979323846;
+    std::vector<double> wd(win);
+    for (int k = 0; k < win; ++k) wd[k] = 0.5 - 0.5 * cos(2.0 * PI * k / win);   // periodic hann (base.py:22-24)
+    // forward: Sf[t][f] = sum_k x[t*hop - win/2 + k] w[k] e^{-2 pi i f (k + padl) / N}
+    std::vector<float> dft;
+    Packer::init_gemm(f.dft, 2 * F, win, dft);
+    for (int k = 0; k < win; ++k)
+        for (int ff = 0; ff < F; ++ff) {
+            const long long ph = ((long long)ff * (k + padl)) % N;
+            const double a = 2.0 * PI * (double)ph / N;
+            dft[(size_t)k * f.dft.ldw + ff] = (float)(wd[k] * cos(a));
+            dft[(size_t)k * f.dft.ldw + F + ff] = (float)(-wd[k] * sin(a));
+        }
+    P.put(&f.dft.wt, dft);
+    // inverse: chunk j of `hop` samples sums frames j-dt, dt < nov; row = dt*2F + cf, col = r; window tap k = dt*hop + r
+    std::vector<float> idft;
+    Packer::init_gemm(f.idft, hop, h->nov * 2 * F, idft);
+    for (int dt = 0; dt < h->nov; ++dt)
+        for (int r = 0; r < hop; ++r) {
+            const int k = dt * hop + r, n = k + padl;
+            for (int ff = 0; ff < F; ++ff) {
+                const long long ph = ((long long)ff * n) % N;
+                const double a = 2.0 * PI * (double)ph / N;
+                const bool edge = (ff == 0) || (2 * ff == N);
+                const double cr = (edge ? 1.0 : 2.0) * cos(a) / N;
+                const double ci = edge ? 0.0 : -2.0 * sin(a) / N;
+                idft[(size_t)(dt * 2 * F + ff) * f.idft.ldw + r] = (float)(wd[k] * cr);
+                idft[(size_t)(dt * 2 * F + F + ff) * f.idft.ldw + r] = (float)(wd[k] * ci);
+            }
+        }
+    P.put(&f.idft.wt, idft);
+    std::vector<float> wsq(win);
+    for (int k = 0; k < win; ++k) { const float wf = (float)wd[k]; wsq[k] = wf * wf; }
+    P.put(&f.wsq, wsq);
+    // patch embedding (scale.py:38,44): conv weight (C0, 2, pf, pt) is already [C0][k], k = (c*pf + s1)*pt + s2
+    P.put(&f.embed_w, P.w("encoder.patch_embed.proj.weight"));
+    P.put(&f.embed_b, P.w("encoder.patch_embed.proj.bias"));
+    P.put_ln(f.embed_ln, "encoder.patch_embed.norm", C0);
+    // de_proj1 (scale.py:66-68): K = tap*ldc(C0) + c
+    const int ld0 = ldc(C0), N1 = C0 * h->pf * h->pt;
+    const std::vector<float>& w1 = P.w("decoder.patch_deembed.de_proj1.weight");
+    std::vector<float> de1;
+    Packer::init_gemm(f.de1, N1, 25 * ld0, de1);
+    for (int n = 0; n < N1; ++n)
+        for (int c = 0; c < C0; ++c)
+            for (int tap = 0; tap < 25; ++tap)
+                de1[(size_t)(tap * ld0 + c) * f.de1.ldw + n] = w1[((size_t)n * C0 + c) * 25 + tap];
+    P.put(&f.de1.wt, de1);
+    P.put(&f.de1.bias, P.w("decoder.patch_deembed.de_proj1.bias"));
+    // de_proj2 (scale.py:70-71): wp[tap][c][2]
+    const std::vector<float>& w2 = P.w("decoder.patch_deembed.de_proj2.weight");
+    std::vector<float> de2((size_t)9 * C0 * 2);
+    for (int o = 0; o < 2; ++o)
+        for (int c = 0; c < C0; ++c)
+            for (int tap = 0; tap < 9; ++tap) de2[((size_t)tap * C0 + c) * 2 + o] = w2[((size_t)o * C0 + c) * 9 + tap];
+    P.put(&f.de2_w, de2);
+    P.put(&f.de2_b, P.w("decoder.patch_deembed.de_proj2.bias"));
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct Bump {
+    char* base;
+    size_t cap, off = 0;
+    bool dry;
+    Bump(void* p, size_t c) : base((char*)p), cap(c), dry(p == nullptr) {}
+    template <class T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* r = dry ? nullptr : (T*)(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    bool ok() const { return dry || off <= cap; }
+};
+
+// Every buffer one encode / decode / forward call needs for `B` clips of `W` time patches.
+struct Work {
+    float* Sf = nullptr;                       // [B][T][2F] frame-major spectrum (STFT out / de-embed out)
+    float* enc[ESCB_MAX_LEVELS] = {};          // encoder outputs per level, [B*H_l*W][ldc(C_l)]
+    float* dec[ESCB_MAX_LEVELS] = {};          // decoder state per level
+    float* xw = nullptr;                       // working token map of the running TransformerLayer
+    float* post = nullptr;                     // post_nn working map
+    float* qkv = nullptr;
+    float* att = nullptr;
+    float* hid = nullptr;
+    float* ze = nullptr;                       // projected VQ vectors [B*T][ldc(3d)]
+    float* Y1 = nullptr;                       // de-embed pixel map [B][F][2W][ldc(C0)]
+    long long* codes = nullptr;                // forward(): internal codes when the caller passes none
+    float* dense = nullptr;                    // staging for the unit entry points
+    float* stage = nullptr;
+};
+
+enum { WK_ENC = 1, WK_DEC = 2, WK_UNIT = 4 };
+
+static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp, Work& wk) {
+    const int L = h->L;
+    const int Wp = round_up(W, 4);
+    size_t max_tok = 0, max_qkv = 0, max_att = 0, max_hid = 0;
+    for (int l = 0; l < L; ++l) {
+        const int C = h->lev[l].C, H = h->lev[l].H, Hp = round_up(H, 4);
+        const size_t M = (size_t)B * H * W, Mw = (size_t)B * Hp * Wp;
+        max_tok = std::max(max_tok, M * ldc(C));
+        max_qkv = std::max(max_qkv, Mw * ldc(3 * C));
+        max_att = std::max(max_att, Mw * ldc(C));
+        max_hid = std::max(max_hid, M * (size_t)(C * h->cfg.mlp_hidden_mult));
+    }
+    wk.Sf = bp.take<float>((size_t)B * std::max(T, h->pt * W) * 2 * h->F);
+    if (what & WK_ENC)
+        for (int l = 0; l < L; ++l) wk.enc[l] = bp.take<float>((size_t)B * h->lev[l].H * W * ldc(h->lev[l].C));
+    for (int l = 0; l < L; ++l) wk.dec[l] = bp.take<float>((size_t)B * h->lev[l].H * W * ldc(h->lev[l].C));
+    wk.xw = bp.take<float>(max_tok);
+    wk.post = bp.take<float>((size_t)B * h->lev[0].H * W * ldc(h->C0));
+    wk.qkv = bp.take<float>(max_qkv);
+    wk.att = bp.take<float>(max_att);
+    wk.hid = bp.take<float>(max_hid);
+    int dmax = 0;
+    for (int q = 0; q < L; ++q) dmax = std::max(dmax, h->cfg.codebook_dims[q]);
+    wk.ze = bp.take<float>((size_t)B * (W / 2) * ldc(3 * dmax));
+    if (what & WK_DEC) wk.Y1 = bp.take<float>((size_t)B * h->F * h->pt * W * ldc(h->C0));
+    wk.codes = bp.take<long long>((size_t)B * L * 3 * (W / 2));
+    if (what & WK_UNIT) {
+        wk.dense = bp.take<float>(std::max(max_tok, (size_t)B * std::max(T, h->pt * W) * 2 * h->F));
+        wk.stage = bp.take<float>(max_tok);
+    }
+    return bp.off;
+}
+
+// ------------------------------------------------------------------------------------------------ drivers
+struct Ctx {
+    escb_handle* h;
+    Launcher L;
+    Work wk;
+    int B, W;
+};
+
+static WindowGeom geom(int H, int W, int shift) {
+    WindowGeom g;
+    g.H = H; g.W = W; g.Hp = round_up(H, 4); g.Wp = round_up(W, 4); g.shift = shift;
+    g.nWw = g.Wp / 4; g.nW = (g.Hp / 4) * g.nWw;
+    return g;
+}
+
+// TransformerLayer.forward (attention.py:48-91).  Reads x_in (never written), runs the blocks in `xw`, then
+// writes the resampled map to `out` (scale != 0) — for scale == 0 the result is left in xw.
+static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, int H) {
+    const LayerW& lw = c.h->layers[li];
+    const int C = lw.C, ld = ldc(C), ldq = ldc(3 * C), ldh = C * c.h->cfg.mlp_hidden_mult;
+    const int B = c.B, W = c.W;
+    const long long M = (long long)B * H * W;
+    const float* src = x_in;
+    for (int j = 0; j < lw.depth; ++j) {
+        const WindowGeom g = geom(H, W, (j & 1) ? 2 : 0);
+        const long long nwin = (long long)B * g.nW, Mw = nwin * 16;
+        const BlockW& bw = lw.blk[j];
+        op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
+        op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, C, nwin, (j & 1) != 0, g);
+        op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
+        op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
+        op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);
+        src = xw;
+    }
+    if (lw.scale == 1) op_merge(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim));
+    else if (lw.scale == 2) op_split(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim));
+}
+
+// Encoder.forward (base.py:143-158) from the frame-major spectrum in wk.Sf.
+static void run_encoder(Ctx& c, int T) {
+    escb_handle* h = c.h;
+    const int L = h->L;
+    op_patch_embed(c.L, h->front, c.wk.Sf, c.B, T, h->lev[0].H, c.W, c.wk.xw, ldc(h->C0));
+    run_layer(c, 0, c.wk.xw, c.wk.enc[0], nullptr, h->lev[0].H);             // pre_nn: result stays in enc[0]
+    for (int i = 0; i < L - 1; ++i) run_layer(c, 1 + i, c.wk.enc[i], c.wk.xw, c.wk.enc[i + 1], h->lev[i].H);
+}
+
+static void pvq_encode(Ctx& c, int q, const float* enc, const float* dec, long long* codes, int S, int s) {
+    const QuantW& qw = c.h->quants[q];
+    const int T = c.W / 2, ldz = ldc(3 * qw.d);
+    op_pvq_down(c.L, qw, enc, dec, c.B, c.W, c.wk.ze, ldz);
+    op_argmin(c.L, qw, 0, 3, c.wk.ze, ldz, (long long)c.B * T, codes + (long long)s * 3 * T, T, (long long)S * 3 * T);
+}
+
+// CrossScaleRVQDecoder.encode (csrvq.py:131-158)
+static void run_csrvq_encode(Ctx& c, int S, long long* codes) {
+    escb_handle* h = c.h;
+    const int L = h->L;
+    pvq_encode(c, 0, c.wk.enc[L - 1], nullptr, codes, S, 0);
+    if (S == 1) return;
+    op_pvq_up(c.L, h->quants[0], codes, S, 0, nullptr, c.B, c.W, c.wk.dec[L - 1]);
+    for (int i = 0; i < S - 1; ++i) {
+        const int lv = L - 1 - i;
+        pvq_encode(c, i + 1, c.wk.enc[lv], c.wk.dec[lv], codes, S, i + 1);
+        if (i + 2 == S) break;
+        op_pvq_up(c.L, h->quants[i + 1], codes, S, i + 1, c.wk.dec[lv], c.B, c.W, c.wk.dec[lv]);
+        run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
+    }
+}
+
+// post_nn + PatchDeEmbed + inverse STFT (csrvq.py:181-182, scale.py:73-81, base.py:39-47) from wk.dec[0]
+static void run_backend(Ctx& c, float* audio, float* recon_feat) {
+    escb_handle* h = c.h;
+    const int H0 = h->lev[0].H, T2 = h->pt * c.W;
+    run_layer(c, 2 * h->L - 1, c.wk.dec[0], c.wk.post, nullptr, H0);
+    op_deembed(c.L, h->front, c.wk.post, ldc(h->C0), c.B, H0, c.W, c.wk.Y1, c.wk.Sf);
+    if (recon_feat) op_transpose(c.L, c.wk.Sf, recon_feat, c.B, T2, 2 * h->F);
+    if (audio) op_istft(c.L, h->front, c.wk.Sf, c.B, T2, audio);
+}
+
+// CrossScaleRVQDecoder.decode (csrvq.py:160-182)
+static void run_csrvq_decode(Ctx& c, int S, const long long* codes) {
+    escb_handle* h = c.h;
+    const int L = h->L;
+    op_pvq_up(c.L, h->quants[0], codes, S, 0, nullptr, c.B, c.W, c.wk.dec[L - 1]);
+    for (int i = 0; i < L - 1; ++i) {
+        const int lv = L - 1 - i;
+        if (i < S - 1) op_pvq_up(c.L, h->quants[i + 1], codes, S, i + 1, c.wk.dec[lv], c.B, c.W, c.wk.dec[lv]);
+        run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
+    }
+}
+
+// CrossScaleRVQDecoder.forward in eval mode (csrvq.py:97-129, 23-48): quantize and decode in one sweep.
+static void run_csrvq_forward(Ctx& c, int S, long long* codes, float* loss) {
+    escb_handle* h = c.h;
+    const int L = h->L, T = c.W / 2;
+    auto vq = [&](int q, const float* enc, const float* dec, float* out) {
+        const QuantW& qw = h->quants[q];
+        pvq_encode(c, q, enc, dec, codes, S, q);
+        if (loss) op_vq_loss(c.L, qw, c.wk.ze, ldc(3 * qw.d), codes, S, q, c.B, T, loss);
+        op_pvq_up(c.L, qw, codes, S, q, dec, c.B, c.W, out);
+    };
+    vq(0, c.wk.enc[L - 1], nullptr, c.wk.dec[L - 1]);
+    for (int i = 0; i < L - 1; ++i) {
+        const int lv = L - 1 - i;
+        if (i < S - 1) vq(i + 1, c.wk.enc[lv], c.wk.dec[lv], c.wk.dec[lv]);
+        run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
+    }
+}
+
+static int check_ready(const escb_handle* h) {
+    if (!h) return fail(ESCB_EINVAL, "null handle");
+    if (!h->finalized) return fail(ESCB_ESTATE, "escb_finalize() has not been called since the last weight change");
+    return ESCB_OK;
+}
+
+static int frames_of(const escb_handle* h, int64_t num_samples) { return (int)(1 + num_samples / h->hop); }
+
+static int time_patches(const escb_handle* h, int64_t num_samples, int* W) {
+    if (num_samples <= h->n_fft / 2)
+        return fail(ESCB_EINVAL, "clip of %lld samples is too short for reflect padding of %d", (long long)num_samples,
+                    h->n_fft / 2);
+    const int T = frames_of(h, num_samples);
+    const int w = (T - h->pt) / h->pt + 1;       // conv stride pt, kernel pt (scale.py:38)
+    if (w <= 0 || w % h->cfg.overlap)
+        return fail(ESCB_EINVAL, "Time dimension must be multiple of overlap (W=%d, overlap=%d)", w, h->cfg.overlap);
+    *W = w;
+    return ESCB_OK;
+}
+
+static int finish(Ctx& c, const char* what) {
+    c.h->launches += c.L.launches;
+    if (c.L.err != cudaSuccess) return fail(ESCB_ECUDA, "%s: %s", what, cudaGetErrorString(c.L.err));
+    return ESCB_OK;
+}
+
+static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (B <= 0) return fail(ESCB_EINVAL, "batch must be positive");
+    if (W <= 0 || W % h->cfg.overlap) return fail(ESCB_EINVAL, "Time dimension must be multiple of overlap (W=%d)", W);
+    c.h = h;
+    c.B = B;
+    c.W = W;
+    c.L.st = (cudaStream_t)stream;
+    Bump dry(nullptr, 0);
+    Work tmp;
+    const size_t need = plan(h, B, W, T, what, dry, tmp);
+    if (!ws || ws_bytes < need)
+        return fail(ESCB_ENOMEM, "workspace of %zu bytes is too small, %zu needed", ws_bytes, need);
+    Bump bp(ws, ws_bytes);
+    plan(h, B, W, T, what, bp, c.wk);
+    return ESCB_OK;
+}
+
+}  // namespace escb
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int escb_abi_version(void) { return ESCB_ABI_VERSION; }
+const char* escb_last_error(void) { return g_err.c_str(); }
+
+int escb_create(const escb_config* cfg, escb_handle** out) {
+    if (!cfg || !out) return fail(ESCB_EINVAL, "null argument");
+    *out = nullptr;
+    const escb_config& c = *cfg;
+    if (c.num_levels < 2 || c.num_levels > ESCB_MAX_LEVELS) return fail(ESCB_EINVAL, "num_levels must be in [2, %d]", ESCB_MAX_LEVELS);
+    if (c.swin_depth < 1 || c.swin_depth > ESCB_MAX_DEPTH) return fail(ESCB_EINVAL, "swin_depth must be in [1, %d]", ESCB_MAX_DEPTH);
+    if (c.window_size != 4) return fail(ESCB_EINVAL, "window_size must be 4");
+    if (c.group_size != 3) return fail(ESCB_EINVAL, "group_size must be 3");
+    if (c.overlap != 2) return fail(ESCB_EINVAL, "overlap must be 2");
+    if (!c.l2norm) return fail(ESCB_EINVAL, "l2norm=False is not supported");
+    if (c.patch_freq < 1 || c.patch_time < 1 || 2 * c.patch_freq * c.patch_time > kEmbedMaxK)
+        return fail(ESCB_EINVAL, "unsupported patch size (%d, %d)", c.patch_freq, c.patch_time);
+    if (c.in_freq < 2 || c.in_freq % c.patch_freq) return fail(ESCB_EINVAL, "in_freq must be a multiple of patch_freq");
+    if (c.mlp_hidden_mult < 1) return fail(ESCB_EINVAL, "mlp_hidden_mult must be >= 1");
+    if (c.codebook_size < 1) return fail(ESCB_EINVAL, "codebook_size must be positive");
+    const int n_fft = 2 * (c.in_freq - 1);
+    if (c.win_length > n_fft || c.win_length < 1 || c.hop_length < 1 || c.win_length % c.hop_length ||
+        (n_fft - c.win_length) % 2 || (c.hop_length & 3))
+        return fail(ESCB_EINVAL, "unsupported STFT geometry (n_fft=%d win=%d hop=%d)", n_fft, c.win_length, c.hop_length);
+    if ((n_fft / 2 - (n_fft - c.win_length) / 2) % c.hop_length)
+        return fail(ESCB_EINVAL, "window support must start on a hop boundary");
+    if (c.h_dims[0] > kEmbedMaxC) return fail(ESCB_EINVAL, "h_dims[0] must be <= %d", kEmbedMaxC);
+    int top = c.in_freq / c.patch_freq;
+    for (int l = 0; l < c.num_levels; ++l) {
+        if (c.h_dims[l] < 1) return fail(ESCB_EINVAL, "h_dims[%d] must be positive", l);
+        if (l < c.num_levels - 1 && (top >> l) % 2) return fail(ESCB_EINVAL, "odd frequency-patch counts are not supported");
+        if (l > 0 && (c.h_dims[l] & 3)) return fail(ESCB_EINVAL, "h_dims[%d] must be a multiple of 4", l);
+        if (c.codebook_dims[l] < 1 || c.codebook_dims[l] > 64) return fail(ESCB_EINVAL, "codebook_dims[%d] must be in [1, 64]", l);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(ESCB_ENODEV, "no usable CUDA device (libescb200 has no CPU fallback)");
+    }
+    escb_handle* h = new escb_handle();
+    h->cfg = c;
+    cudaGetDevice(&h->device);
+    h->L = c.num_levels;
+    h->F = c.in_freq; h->n_fft = n_fft; h->win = c.win_length; h->hop = c.hop_length;
+    h->pf = c.patch_freq; h->pt = c.patch_time; h->C0 = c.h_dims[0]; h->nov = c.win_length / c.hop_length;
+    for (int l = 0; l < h->L; ++l) h->lev[l] = {c.h_dims[l], top >> l};
+    for (int li = 0; li < 2 * h->L; ++li) {
+        const LayerDesc d = layer_desc(h, li);
+        if (d.heads < 1 || d.C % d.heads || 16 * d.heads > 1024 || !attention_supported(d.C / d.heads)) {
+            const int code = fail(ESCB_EINVAL, "%s: %d channels / %d heads has no attention kernel", d.prefix.c_str(), d.C, d.heads);
+            delete h;
+            return code;
+        }
+    }
+    build_manifest(h);
+    const cudaError_t e = swin_init();
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(ESCB_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return ESCB_OK;
+}
+
+void escb_destroy(escb_handle* h) {
+    if (!h) return;
+    if (h->arena) cudaFree(h->arena);
+    if (h->host_scratch) cudaFree(h->host_scratch);
+    delete h;
+}
+
+int escb_num_weights(const escb_handle* h) { return h ? (int)h->weights.size() : 0; }
+const char* escb_weight_name(const escb_handle* h, int i) {
+    return (h && i >= 0 && i < (int)h->weights.size()) ? h->weights[i].name.c_str() : nullptr;
+}
+int64_t escb_weight_numel(const escb_handle* h, int i) {
+    return (h && i >= 0 && i < (int)h->weights.size()) ? h->weights[i].numel : -1;
+}
+
+int escb_set_weight(escb_handle* h, const char* name, const float* data, int64_t numel, int is_device) {
+    if (!h || !name || !data) return fail(ESCB_EINVAL, "null argument");
+    auto it = h->index.find(name);
+    if (it == h->index.end()) return fail(ESCB_EKEY, "unknown weight '%s'", name);
+    Weight& w = h->weights[it->second];
+    if (numel != w.numel) return fail(ESCB_EINVAL, "size mismatch for %s: got %lld elements, expected %lld", name,
+                                      (long long)numel, (long long)w.numel);
+    w.host.resize((size_t)numel);
+    if (is_device) {
+        const cudaError_t e = cudaMemcpy(w.host.data(), data, (size_t)numel * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(ESCB_ECUDA, "copy of %s failed: %s", name, cudaGetErrorString(e));
+    } else {
+        memcpy(w.host.data(), data, (size_t)numel * sizeof(float));
+    }
+    w.set = true;
+    h->finalized = false;
+    return ESCB_OK;
+}
+
+int escb_finalize(escb_handle* h) {
+    if (!h) return fail(ESCB_EINVAL, "null handle");
+    for (const Weight& w : h->weights)
+        if (!w.set) return fail(ESCB_ESTATE, "weight '%s' has not been set", w.name.c_str());
+    Packer P{h};
+    for (int li = 0; li < 2 * h->L; ++li) pack_layer(P, li);
+    for (int q = 0; q < h->L; ++q) pack_quant(P, q);
+    pack_front(P);
+    cudaSetDevice(h->device);
+    if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
+    const size_t bytes = P.arena.data.size() * sizeof(float);
+    cudaError_t e = cudaMalloc((void**)&h->arena, bytes);
+    if (e != cudaSuccess) return fail(ESCB_ENOMEM, "cudaMalloc of %zu weight bytes failed: %s", bytes, cudaGetErrorString(e));
+    e = cudaMemcpy(h->arena, P.arena.data.data(), bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "weight upload failed: %s", cudaGetErrorString(e));
+    for (const Fix& f : P.fixes) *f.slot = h->arena + f.off;
+    h->finalized = true;
+    return ESCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+int escb_time_patches(const escb_handle* h, int64_t num_samples, int32_t* W) {
+    if (!h || !W) return fail(ESCB_EINVAL, "null argument");
+    int w = 0;
+    if (int e = time_patches(h, num_samples, &w)) return e;
+    *W = w;
+    return ESCB_OK;
+}
+
+int64_t escb_decoded_samples(const escb_handle* h, int32_t W) { return h ? (int64_t)h->hop * ((int64_t)h->pt * W - 1) : -1; }
+
+int escb_workspace_bytes(const escb_handle* h, int32_t batch, int32_t W, size_t* bytes) {
+    if (!h || !bytes) return fail(ESCB_EINVAL, "null argument");
+    if (batch <= 0 || W <= 0) return fail(ESCB_EINVAL, "batch and W must be positive");
+    Bump dry(nullptr, 0);
+    Work tmp;
+    // frames of the longest clip that yields W patches: pt*W + pt - 1
+    *bytes = plan(h, batch, W, h->pt * W + h->pt - 1, WK_ENC | WK_DEC | WK_UNIT, dry, tmp) + 256;
+    return ESCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hot path
+int escb_encode(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int32_t S, int64_t* codes, void* ws,
+                size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!audio || !codes) return fail(ESCB_EINVAL, "null argument");
+    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    int W = 0;
+    if (int e = time_patches(h, Ls, &W)) return e;
+    const int T = frames_of(h, Ls);
+    Ctx c;
+    if (int e = begin(h, c, B, W, T, WK_ENC, ws, ws_bytes, stream)) return e;
+    op_stft(c.L, h->front, audio, B, Ls, T, c.wk.Sf);
+    run_encoder(c, T);
+    run_csrvq_encode(c, S, (long long*)codes);
+    return finish(c, "escb_encode");
+}
+
+int escb_decode(escb_handle* h, const int64_t* codes, int32_t B, int32_t S, int32_t W, float* audio, float* recon_feat,
+                void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!codes || (!audio && !recon_feat)) return fail(ESCB_EINVAL, "null argument");
+    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    Ctx c;
+    if (int e = begin(h, c, B, W, h->pt * W, WK_DEC, ws, ws_bytes, stream)) return e;
+    run_csrvq_decode(c, S, (const long long*)codes);
+    run_backend(c, audio, recon_feat);
+    return finish(c, "escb_decode");
+}
+
+int escb_forward(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int32_t S, int64_t* codes, float* audio_out,
+                 float* raw_feat, float* recon_feat, float* vq_loss, void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!audio) return fail(ESCB_EINVAL, "null argument");
+    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    int W = 0;
+    if (int e = time_patches(h, Ls, &W)) return e;
+    const int T = frames_of(h, Ls);
+    Ctx c;
+    if (int e = begin(h, c, B, W, T, WK_ENC | WK_DEC, ws, ws_bytes, stream)) return e;
+    op_stft(c.L, h->front, audio, B, Ls, T, c.wk.Sf);
+    if (raw_feat) op_transpose(c.L, c.wk.Sf, raw_feat, B, T, 2 * h->F);
+    run_encoder(c, T);
+    if (vq_loss) {
+        const cudaError_t e = cudaMemsetAsync(vq_loss, 0, (size_t)B * sizeof(float), c.L.st);
+        if (e != cudaSuccess && c.L.err == cudaSuccess) c.L.err = e;
+    }
+    run_csrvq_forward(c, S, codes ? (long long*)codes : c.wk.codes, vq_loss);
+    run_backend(c, audio_out, recon_feat);
+    return finish(c, "escb_forward");
+}
+
+// Host-buffer variants: H2D, run, D2H, synchronise.
+static int host_scratch(escb_handle* h, size_t bytes, void** p) {
+    if (h->host_scratch_bytes < bytes) {
+        if (h->host_scratch) cudaFree(h->host_scratch);
+        h->host_scratch = nullptr;
+        h->host_scratch_bytes = 0;
+        const cudaError_t e = cudaMalloc(&h->host_scratch, bytes);
+        if (e != cudaSuccess) return fail(ESCB_ENOMEM, "cudaMalloc of %zu scratch bytes failed: %s", bytes, cudaGetErrorString(e));
+        h->host_scratch_bytes = bytes;
+    }
+    *p = h->host_scratch;
+    return ESCB_OK;
+}
+
+int escb_encode_host(escb_handle* h, const float* audio_host, int32_t B, int64_t Ls, int32_t S, int64_t* codes_host,
+                     void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!audio_host || !codes_host) return fail(ESCB_EINVAL, "null argument");
+    if (B <= 0) return fail(ESCB_EINVAL, "batch must be positive");
+    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    int W = 0;
+    if (int e = time_patches(h, Ls, &W)) return e;
+    size_t ws = 0;
+    if (int e = escb_workspace_bytes(h, B, W, &ws)) return e;
+    const size_t a_bytes = align_up((size_t)B * Ls * sizeof(float), 256);
+    const size_t c_bytes = align_up((size_t)B * S * 3 * (W / 2) * sizeof(int64_t), 256);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    void* base = nullptr;
+    if (int e = host_scratch(h, a_bytes + c_bytes + ws, &base)) return e;
+    float* a_dev = (float*)base;
+    int64_t* c_dev = (int64_t*)((char*)base + a_bytes);
+    void* w_dev = (char*)base + a_bytes + c_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(a_dev, audio_host, (size_t)B * Ls * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    if (int r = escb_encode(h, a_dev, B, Ls, S, c_dev, w_dev, ws, stream)) return r;
+    e = cudaMemcpyAsync(codes_host, c_dev, (size_t)B * S * 3 * (W / 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "escb_encode_host: %s", cudaGetErrorString(e));
+    return ESCB_OK;
+}
+
+int escb_decode_host(escb_handle* h, const int64_t* codes_host, int32_t B, int32_t S, int32_t W, float* audio_host,
+                     void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!codes_host || !audio_host) return fail(ESCB_EINVAL, "null argument");
+    if (B <= 0 || W <= 0) return fail(ESCB_EINVAL, "batch and W must be positive");
+    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    size_t ws = 0;
+    if (int e = escb_workspace_bytes(h, B, W, &ws)) return e;
+    const int64_t n_out = escb_decoded_samples(h, W);
+    const size_t a_bytes = align_up((size_t)B * n_out * sizeof(float), 256);
+    const size_t c_bytes = align_up((size_t)B * S * 3 * (W / 2) * sizeof(int64_t), 256);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    void* base = nullptr;
+    if (int e = host_scratch(h, a_bytes + c_bytes + ws, &base)) return e;
+    float* a_dev = (float*)base;
+    int64_t* c_dev = (int64_t*)((char*)base + a_bytes);
+    void* w_dev = (char*)base + a_bytes + c_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(c_dev, codes_host, (size_t)B * S * 3 * (W / 2) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    if (int r = escb_decode(h, c_dev, B, S, W, a_dev, nullptr, w_dev, ws, stream)) return r;
+    e = cudaMemcpyAsync(audio_host, a_dev, (size_t)B * n_out * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "escb_decode_host: %s", cudaGetErrorString(e));
+    return ESCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ unit entry points
+int escb_stft(escb_handle* h, const float* audio, int32_t B, int64_t Ls, float* planes, void* ws, size_t ws_bytes,
+              void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!audio || !planes) return fail(ESCB_EINVAL, "null argument");
+    if (Ls <= h->n_fft / 2) return fail(ESCB_EINVAL, "clip too short for reflect padding");
+    const int T = frames_of(h, Ls);
+    Ctx c;
+    if (int e = begin(h, c, B, h->cfg.overlap, T, WK_UNIT, ws, ws_bytes, stream)) return e;
+    op_stft(c.L, h->front, audio, B, Ls, T, c.wk.dense);
+    op_transpose(c.L, c.wk.dense, planes, B, T, 2 * h->F);
+    return finish(c, "escb_stft");
+}
+
+int escb_istft(escb_handle* h, const float* planes, int32_t B, int32_t T, float* audio, void* ws, size_t ws_bytes,
+               void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!audio || !planes) return fail(ESCB_EINVAL, "null argument");
+    if (T < 2) return fail(ESCB_EINVAL, "need at least 2 frames");
+    Ctx c;
+    if (int e = begin(h, c, B, h->cfg.overlap, T, WK_UNIT, ws, ws_bytes, stream)) return e;
+    op_transpose(c.L, planes, c.wk.dense, B, 2 * h->F, T);
+    op_istft(c.L, h->front, c.wk.dense, B, T, audio);
+    return finish(c, "escb_istft");
+}
+
+int escb_patch_embed(escb_handle* h, const float* planes, int32_t B, int32_t T, float* tokens, void* ws,
+                     size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!tokens || !planes) return fail(ESCB_EINVAL, "null argument");
+    const int W = (T - h->pt) / h->pt + 1;
+    if (W <= 0) return fail(ESCB_EINVAL, "too few frames");
+    Ctx c;
+    if (int e = begin(h, c, B, round_up(W, 2), T, WK_UNIT, ws, ws_bytes, stream)) return e;
+    const int H = h->lev[0].H;
+    op_transpose(c.L, planes, c.wk.dense, B, 2 * h->F, T);
+    op_patch_embed(c.L, h->front, c.wk.dense, B, T, H, W, c.wk.xw, ldc(h->C0));
+    op_repitch(c.L, c.wk.xw, ldc(h->C0), tokens, h->C0, h->C0, (long long)B * H * W);
+    return finish(c, "escb_patch_embed");
+}
+
+int escb_patch_deembed(escb_handle* h, const float* tokens, int32_t B, int32_t W, float* planes, void* ws,
+                       size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!tokens || !planes) return fail(ESCB_EINVAL, "null argument");
+    if (W <= 0) return fail(ESCB_EINVAL, "W must be positive");
+    Ctx c;
+    if (int e = begin(h, c, B, round_up(W, 2), h->pt * W, WK_UNIT | WK_DEC, ws, ws_bytes, stream)) return e;
+    const int H = h->lev[0].H;
+    op_repitch(c.L, tokens, h->C0, c.wk.post, ldc(h->C0), h->C0, (long long)B * H * W);
+    op_deembed(c.L, h->front, c.wk.post, ldc(h->C0), B, H, W, c.wk.Y1, c.wk.Sf);
+    op_transpose(c.L, c.wk.Sf, planes, B, h->pt * W, 2 * h->F);
+    return finish(c, "escb_patch_deembed");
+}
+
+int escb_swin_layer(escb_handle* h, int32_t li, const float* x, int32_t B, int32_t H, int32_t W, float* y, void* ws,
+                    size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!x || !y) return fail(ESCB_EINVAL, "null argument");
+    if (li < 0 || li >= 2 * h->L) return fail(ESCB_EINVAL, "layer_index out of range");
+    const LayerDesc d = layer_desc(h, li);
+    if (H != d.H) return fail(ESCB_EINVAL, "layer %s runs at H=%d, got %d", d.prefix.c_str(), d.H, H);
+    if (W <= 0) return fail(ESCB_EINVAL, "W must be positive");
+    Ctx c;
+    if (int e = begin(h, c, B, round_up(W, 2), h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
+    c.W = W;
+    const long long M = (long long)B * H * W;
+    // stage: dense -> padded rows, run, padded -> dense
+    float* xin = c.wk.stage;
+    op_repitch(c.L, x, d.C, xin, ldc(d.C), d.C, M);
+    float* out = c.wk.dense;
+    run_layer(c, li, xin, c.wk.xw, out, H);
+    const long long Mo = d.scale == 1 ? M / 2 : (d.scale == 2 ? M * 2 : M);
+    op_repitch(c.L, d.scale ? out : c.wk.xw, ldc(d.out_dim), y, d.out_dim, d.out_dim, Mo);
+    return finish(c, "escb_swin_layer");
+}
+
+int escb_pvq_encode(escb_handle* h, int32_t q, const float* enc, const float* dec, int32_t B, int32_t W, int64_t* codes,
+                    void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!enc || !codes) return fail(ESCB_EINVAL, "null argument");
+    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    Ctx c;
+    if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
+    pvq_encode(c, q, enc, dec, (long long*)codes, 1, 0);
+    return finish(c, "escb_pvq_encode");
+}
+
+int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes, const float* dec, int32_t B, int32_t W, float* out,
+                    void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!codes || !out) return fail(ESCB_EINVAL, "null argument");
+    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    Ctx c;
+    if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
+    op_pvq_up(c.L, h->quants[q], (const long long*)codes, 1, 0, dec, B, W, out);
+    return finish(c, "escb_pvq_decode");
+}
+
+int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, int64_t rows, int64_t* idx, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!z || !idx) return fail(ESCB_EINVAL, "null argument");
+    if (q < 0 || q >= h->L || g < 0 || g >= 3) return fail(ESCB_EINVAL, "stream/group index out of range");
+    if (rows <= 0) return ESCB_OK;
+    Ctx c;
+    c.h = h;
+    c.L.st = (cudaStream_t)stream;
+    const QuantW& qw = h->quants[q];
+    op_argmin(c.L, qw, g, 1, z, qw.d, rows, (long long*)idx, (int)std::min<int64_t>(rows, 1 << 30), 0);
+    return finish(c, "escb_codebook_argmin");
+}
+
+int64_t escb_launch_count(const escb_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
+
+}  // extern "C"

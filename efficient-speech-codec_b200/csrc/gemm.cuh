@@ -1,0 +1,249 @@
+// fp32 GEMM engine with fused gather/LayerNorm prologues and scatter/activation epilogues.
+//
+//   Y = epilogue( LN?(gather(A)) [M,K] * Wt [K,N] )
+//
+// Every dense contraction of the ESC hot path (QKV / proj / MLP linears, PatchMerge / PatchSplit, the
+// product-VQ projections, the 5x5 de-embedding conv as implicit GEMM, the DFT / inverse-DFT) is one
+// instantiation of this kernel: the "A loader" describes how a logical row is gathered from HBM (window
+// partition + cyclic shift, frequency-row pairing, VQ frame layout, im2col, STFT framing ...) and the
+// epilogue describes where each output element lands (window reverse, pixel shuffle, overlap-add ...),
+// so none of the reference's permute/contiguous copies (21 % of its CPU time) exist here.
+//
+// Arithmetic is plain fp32 FMA on the CUDA cores: bit-exact RVQ indices need fp32-grade products
+// (SURVEY.md §7 hard part 1).  Tile: (16*TM) x (16*TN) x 16, 256 threads, register double-buffered.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace escb {
+
+constexpr int kBK = 16;
+constexpr int kGemmThreads = 256;
+
+struct LnParams {
+    const float* gamma;   // padded with zeros to a multiple of 4
+    const float* beta;
+    float eps;
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 mask4(float4 v, int k, int K) {
+    if (k + 1 >= K) v.y = 0.f;
+    if (k + 2 >= K) v.z = 0.f;
+    if (k + 3 >= K) v.w = 0.f;
+    return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int TM, int TN, bool LN, class AL, class EP>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const int ldw, const long long M,
+            const int N, const int K, const int Kpad, const int ntn, const EP ep) {
+    constexpr int BM = 16 * TM, BN = 16 * TN;
+    constexpr int AP = BM + 4;
+    constexpr int PA = BM / 64;                         // float4 A loads per thread per k-tile
+    constexpr int NB4 = kBK * BN / 4;
+    constexpr int PB = (NB4 + kGemmThreads - 1) / kGemmThreads;
+
+    __shared__ __align__(16) float As[2][kBK][AP];
+    __shared__ __align__(16) float Bs[2][kBK][BN];
+    __shared__ typename AL::Row rows[BM];
+    __shared__ float2 stats[LN ? BM : 1];
+
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)(blockIdx.x / ntn) * BM;
+    const int n0 = (blockIdx.x % ntn) * BN;
+
+    for (int r = tid; r < BM; r += kGemmThreads) al.init(m0 + r, M, rows[r]);
+    __syncthreads();
+
+    if (LN) {   // per-row mean / rstd, two-pass, one warp per row
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < BM; r += kGemmThreads / 32) {
+            const typename AL::Row row = rows[r];
+            float mean = 0.f, rstd = 0.f;
+            if (al.valid(row)) {
+                float s = 0.f;
+                for (int k = lane; k < K; k += 32) s += al.load1(row, k);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                mean = s / (float)K;
+                float q = 0.f;
+                for (int k = lane; k < K; k += 32) { const float d = al.load1(row, k) - mean; q = fmaf(d, d, q); }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                rstd = 1.0f / sqrtf(q / (float)K + ln.eps);
+            }
+            if (lane == 0) stats[r] = make_float2(mean, rstd);
+        }
+        __syncthreads();
+    }
+
+    const int tx = tid & 15, ty = tid >> 4;
+    const int a_kq = (tid & 3) * 4, a_r = tid >> 2;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 a_reg[PA], b_reg[PB];
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int p = 0; p < PA; ++p) {
+            const int r = a_r + 64 * p;
+            const typename AL::Row row = rows[r];
+            const int k = k0 + a_kq;
+            float4 v = zero4();
+            if (al.valid(row) && k < K) {
+                v = al.load4(row, k, K);
+                if (LN) {
+                    const float2 st = stats[r];
+                    const float4 g = ldg4(ln.gamma + k), b = ldg4(ln.beta + k);
+                    v.x = (v.x - st.x) * st.y * g.x + b.x;
+                    v.y = (v.y - st.x) * st.y * g.y + b.y;
+                    v.z = (v.z - st.x) * st.y * g.z + b.z;
+                    v.w = (v.w - st.x) * st.y * g.w + b.w;
+                    v = mask4(v, k, K);
+                }
+            }
+            a_reg[p] = v;
+        }
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const int idx = tid + kGemmThreads * p;
+            float4 v = zero4();
+            if (idx < NB4) {
+                const int kk = idx / (BN / 4), nq = idx % (BN / 4);
+                const int n = n0 + nq * 4;
+                if (n < ldw) v = ldg4(Wt + (long long)(k0 + kk) * ldw + n);
+            }
+            b_reg[p] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int p = 0; p < PA; ++p) {
+            const int r = a_r + 64 * p;
+            As[buf][a_kq + 0][r] = a_reg[p].x;
+            As[buf][a_kq + 1][r] = a_reg[p].y;
+            As[buf][a_kq + 2][r] = a_reg[p].z;
+            As[buf][a_kq + 3][r] = a_reg[p].w;
+        }
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            const int idx = tid + kGemmThreads * p;
+            if (idx < NB4) {
+                const int kk = idx / (BN / 4), nq = idx % (BN / 4);
+                *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = b_reg[p];
+            }
+        }
+    };
+
+    const int nk = Kpad / kBK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) load_tiles((kt + 1) * kBK);
+#pragma unroll
+        for (int kk = 0; kk < kBK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&As[cur][kk][ty * TM + i]);
+                a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[cur][kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store_tiles(cur ^ 1);
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        typename EP::Row er;
+        if (!ep.row(m, er)) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n < N) ep.store(er, n, acc[i][j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be null
+    const float* wt;
+    const float* bias;
+    int N, K, Kpad, ldw;
+};
+
+inline int pick_tn(int N) {
+    const int cand[6] = {3, 5, 6, 7, 8, 9};
+    int best = 3;
+    long long best_pad = -1;
+    for (int c : cand) {
+        const int bn = 16 * c;
+        const long long pad = (long long)((N + bn - 1) / bn) * bn;
+        if (best_pad < 0 || pad < best_pad || (pad == best_pad && c > best)) { best = c; best_pad = pad; }
+    }
+    return best;
+}
+
+template <int TM, int TN, bool LN, class AL, class EP>
+inline cudaError_t launch_gemm_t(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& w,
+                                 long long M, const EP& ep) {
+    constexpr int BM = 16 * TM, BN = 16 * TN;
+    const int ntn = (w.N + BN - 1) / BN;
+    const long long ntm = (M + BM - 1) / BM;
+    if (ntm <= 0) return cudaSuccess;
+    gemm_kernel<TM, TN, LN, AL, EP><<<(unsigned)(ntm * ntn), kGemmThreads, 0, st>>>(
+        al, ln, w.wt, w.ldw, M, w.N, w.K, w.Kpad, ntn, ep);
+    return cudaGetLastError();
+}
+
+// Instantiates only the TN values listed in the TNS... pack (keeps compile time bounded); TN is chosen by
+// pick_tn among them, TM by the number of row tiles (small problems get the 64-row tile to fill 148 SMs).
+template <bool LN, class AL, class EP, int... TNS>
+struct GemmLauncher {
+    template <int TN>
+    static cudaError_t go(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& w, long long M,
+                          const EP& ep) {
+        const int ntn = (w.N + 16 * TN - 1) / (16 * TN);
+        if (((M + 127) / 128) * ntn >= 2 * 148) return launch_gemm_t<8, TN, LN, AL, EP>(st, al, ln, w, M, ep);
+        return launch_gemm_t<4, TN, LN, AL, EP>(st, al, ln, w, M, ep);
+    }
+    static cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& w, long long M,
+                              const EP& ep) {
+        // best TN among the instantiated ones
+        const int list[] = {TNS...};
+        int best = list[0];
+        long long best_pad = -1;
+        for (int c : list) {
+            const int bn = 16 * c;
+            const long long pad = (long long)((w.N + bn - 1) / bn) * bn;
+            if (best_pad < 0 || pad < best_pad || (pad == best_pad && c > best)) { best = c; best_pad = pad; }
+        }
+        cudaError_t err = cudaErrorInvalidValue;
+        const bool hit = ((best == TNS ? (err = go<TNS>(st, al, ln, w, M, ep), true) : false) || ...);
+        (void)hit;
+        return err;
+    }
+};
+
+}  // namespace escb

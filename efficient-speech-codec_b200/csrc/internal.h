@@ -1,0 +1,88 @@
+// Internal (non-ABI) declarations shared by the translation units of libescb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/escb200.h"
+#include "gemm.cuh"
+#include "loaders.cuh"
+
+namespace escb {
+
+inline int ldc(int C) { return (C + 3) & ~3; }
+
+struct LnW { const float* g; const float* b; };     // padded to a multiple of 4 with zeros
+
+struct BlockW {
+    LnW n1, n2;
+    GemmWeight qkv, proj, fc1, fc2;
+    const float* relbias;                            // [heads][16][16], gathered from the (49, heads) table
+};
+
+struct LayerW {
+    int C, heads, hd, depth, scale, out_dim;         // scale: 0 none, 1 down (PatchMerge), 2 up (PatchSplit)
+    BlockW blk[ESCB_MAX_DEPTH];
+    LnW sn;
+    GemmWeight sub;
+};
+
+struct QuantW {
+    int in_dim, in_freq, d, frame_dim, ncodes;
+    GemmWeight down;                                 // K = frame_dim in (h,o,c) order, N = 3d (block structured)
+    GemmWeight up;                                   // K = 3d, N = frame_dim in (h,o,c) order
+    const float* raw;                                // [3][ncodes][d]
+    const float* cbn;                                // [3][ncodes][d] L2-normalised
+    const float* cnorm;                              // [3][ncodes] squared norms of cbn rows
+};
+
+struct FrontW {
+    int F, win, hop, nov, C0, pf, pt;
+    GemmWeight dft;                                  // [win][2F] windowed DFT basis
+    GemmWeight idft;                                 // [nov*2F][hop] windowed inverse basis
+    const float* wsq;                                // [win] squared synthesis window
+    const float* embed_w; const float* embed_b; LnW embed_ln;
+    GemmWeight de1;                                  // conv5x5 as implicit GEMM, K = 25*ldc(C0)
+    const float* de2_w; const float* de2_b;          // [9][C0][2], [2]
+};
+
+struct Launcher {                                    // stream + launch accounting + first-error latch
+    cudaStream_t st = nullptr;
+    long long launches = 0;
+    cudaError_t err = cudaSuccess;
+    void note(cudaError_t e) { ++launches; if (err == cudaSuccess && e != cudaSuccess) err = e; }
+};
+
+constexpr float kLnEps = 1e-5f;
+constexpr int kEmbedMaxC = 64;     // patch_embed_kernel register budget: h_dims[0] <= 64
+constexpr int kEmbedMaxK = 16;     // 2 * patch_freq * patch_time <= 16
+
+// ---- swin.cu : one reference SwinBlock = qkv -> attention -> proj -> mlp1 -> mlp2
+void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq);
+void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
+                  int hd, int C, long long nwin, bool masked, const WindowGeom& g);
+void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
+             const WindowGeom& g, long long M);
+void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh);
+void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long M, float* x, int ld);
+void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
+void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
+cudaError_t swin_init();
+
+// ---- pvq.cu : product VQ of one stream
+void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz);
+void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const float* ze, int ldz, long long rows,
+               long long* out, int T, long long bstride);
+void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
+               float* out);
+void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
+                int T, float* loss);
+
+// ---- frontend.cu : STFT / patch embed / patch de-embed / inverse STFT / layout helpers
+void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long Ls, int T, float* Sf);
+void op_patch_embed(Launcher& L, const FrontW& f, const float* Sf, int B, int T, int H, int W, float* tok, int ld);
+void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, int H, int W, float* Y1, float* Xf);
+void op_istft(Launcher& L, const FrontW& f, const float* Xf, int B, int T, float* audio);
+void op_transpose(Launcher& L, const float* in, float* out, int B, int R, int C);
+void op_repitch(Launcher& L, const float* src, int lds, float* dst, int ldd, int C, long long rows);
+
+}  // namespace escb

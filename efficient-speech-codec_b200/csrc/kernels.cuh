@@ -1,0 +1,303 @@
+// Non-GEMM kernels of the ESC hot path: window-attention core, codebook argmin, patch embedding,
+// the 3x3 output convolution and small layout helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace escb {
+
+// ------------------------------------------------------------------------------------------------ attention core
+// One thread per (window, head, query token): 16 scores, softmax, 16-term weighted sum of V — all in registers.
+// q/k/v of the block's windows are staged in shared memory with coalesced float4 loads; the 16 lanes that share
+// a head read K/V rows as broadcasts.  Mirrors WindowAttention.forward (attention.py:222-241): q is scaled before
+// the product, the relative-position bias and then the 0/-100 shifted-window mask are added, softmax over keys.
+// qkv rows are window-major (row = window*16 + token), columns [3][heads][HD].
+template <int HD>
+__global__ void window_attn_kernel(const float* __restrict__ qkv, const int ldq, float* __restrict__ out,
+                                   const int ldo, const float* __restrict__ relbias, const int nH, const int C,
+                                   const long long nwin_total, const int wpb, const float scale, const int masked,
+                                   const int nW, const int nWw, const int Hp, const int Wp) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const long long win0 = (long long)blockIdx.x * wpb;
+    const int nwin = (int)((nwin_total - win0 < wpb) ? (nwin_total - win0) : wpb);
+    {
+        const int n4 = nwin * 16 * ldq / 4;
+        const float4* src = reinterpret_cast<const float4*>(qkv + win0 * 16 * (long long)ldq);
+        float4* dst = reinterpret_cast<float4*>(sm);
+        for (int i = tid; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int per_win = 16 * nH;
+    const int lw = tid / per_win;
+    if (lw >= nwin) return;
+    const int r = tid - lw * per_win;
+    const int h = r >> 4, i = r & 15;
+    const float* base = sm + (long long)lw * 16 * ldq;
+
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = base[i * ldq + h * HD + d] * scale;
+
+    float s[16];
+    const float* kb = base + C + h * HD;
+    const float* bias = relbias + (h * 16 + i) * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc = fmaf(q[d], kb[j * ldq + d], acc);
+        s[j] = acc + __ldg(bias + j);
+    }
+    if (masked) {
+        // region ids of the shifted map (attention.py:56-75): 0 | 1 | 2 along each axis, id = 3*rh + rw
+        const int win = (int)((win0 + lw) % nW);
+        const int wh = win / nWw, ww = win - wh * nWw;
+        int rh[4], rw[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int hs = wh * 4 + a, ws = ww * 4 + a;
+            rh[a] = hs < Hp - 4 ? 0 : (hs < Hp - 2 ? 1 : 2);
+            rw[a] = ws < Wp - 4 ? 0 : (ws < Wp - 2 ? 1 : 2);
+        }
+        const int mine = 3 * rh[i >> 2] + rw[i & 3];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (3 * rh[j >> 2] + rw[j & 3] != mine) s[j] += -100.0f;
+    }
+    float mx = s[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, s[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    const float* vb = base + 2 * C + h * HD;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float p = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(p, vb[j * ldq + d], o[d]);
+    }
+    float* op = out + ((win0 + lw) * 16 + i) * (long long)ldo + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) op[d] = o[d];
+}
+
+// ------------------------------------------------------------------------------------------------ RVQ argmin
+// Codebook.quantize_to_code (codebook.py:20-43): z and the table are L2-normalised (x / max(|x|, 1e-12)), the
+// distance is (|z|^2 - (2z).c) + |c|^2 and the FIRST minimum wins.  cbn / cnorm are the normalised table and its
+// squared norms, precomputed once per weight load.  One warp per (row, group): each lane scans 1/32 of the codes in
+// increasing order (strict <), then a lexicographic (dist, index) warp reduction keeps the lowest index on ties.
+// codes are written straight into the [B, S, G, T] tensor.
+template <int D>
+__global__ void codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int zoff, const int d_rt,
+                                       const float* __restrict__ cbn, const float* __restrict__ cnorm,
+                                       const int ncodes, const long long rows, long long* __restrict__ out,
+                                       const int T, const long long bstride, const int groups, const int d_stride) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= rows * groups) return;
+    const long long m = wid / groups;
+    const int g = (int)(wid - m * groups);
+    const int d = D > 0 ? D : d_rt;
+    constexpr int DM = D > 0 ? D : 64;
+    const float* zp = z + m * (long long)ldz + zoff + g * d_stride;
+    float zn[DM];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < DM; ++k)
+        if (k < d) { zn[k] = __ldg(zp + k); ss = fmaf(zn[k], zn[k], ss); }
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    float zz = 0.f;
+#pragma unroll
+    for (int k = 0; k < DM; ++k)
+        if (k < d) { zn[k] = zn[k] / denom; zz = fmaf(zn[k], zn[k], zz); zn[k] = 2.0f * zn[k]; }
+    const float* cb = cbn + (long long)g * ncodes * d;
+    const float* cn = cnorm + (long long)g * ncodes;
+    float best = 3.0e38f;
+    int besti = 0x7fffffff;
+    for (int c = lane; c < ncodes; c += 32) {
+        const float* cp = cb + (long long)c * d;
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < DM; ++k)
+            if (k < d) dot = fmaf(zn[k], __ldg(cp + k), dot);
+        const float dist = (zz - dot) + __ldg(cn + c);
+        if (dist < best) { best = dist; besti = c; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) {
+        if (besti == 0x7fffffff) besti = 0;       // all-NaN row: torch.min returns index 0 of the NaN run start
+        const long long b = m / T;
+        const int t = (int)(m - b * T);
+        out[b * bstride + (long long)g * T + t] = besti;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ patch embedding
+// PatchEmbed.forward (scale.py:42-50): non-overlapping (pf x pt) patches of the 2-plane spectrum -> C0 channels,
+// then LayerNorm(C0).  The spectrum is read frame-major [B, T, 2F]; one thread per token, adjacent threads take
+// adjacent frequency patches so the pf-float reads coalesce.  Weight k index = (c*pf + s1)*pt + s2.
+static __global__ void patch_embed_kernel(const float* __restrict__ Sf, const int T, const int F, float* __restrict__ tok,
+                                   const int ld, const float* __restrict__ w, const float* __restrict__ bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, const int C0,
+                                   const int pf, const int pt, const int H, const int W, const long long total,
+                                   const float eps) {
+    __shared__ float sw[kEmbedMaxC * kEmbedMaxK];
+    __shared__ float sb[kEmbedMaxC], sg[kEmbedMaxC], sbe[kEmbedMaxC];
+    const int KP = 2 * pf * pt;
+    for (int i = threadIdx.x; i < C0 * KP; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < C0; i += blockDim.x) { sb[i] = bias[i]; sg[i] = gamma[i]; sbe[i] = beta[i]; }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int h = (int)(idx % H);
+    const int wq = (int)((idx / H) % W);
+    const long long b = idx / ((long long)H * W);
+    float in[kEmbedMaxK];
+#pragma unroll
+    for (int k = 0; k < kEmbedMaxK; ++k) {
+        if (k < KP) {
+            const int c = k / (pf * pt), rem = k - c * pf * pt;
+            const int s1 = rem / pt, s2 = rem - s1 * pt;
+            in[k] = __ldg(Sf + (b * T + (long long)wq * pt + s2) * (2 * F) + c * F + h * pf + s1);
+        } else in[k] = 0.f;
+    }
+    float y[kEmbedMaxC];
+    float s = 0.f;
+#pragma unroll
+    for (int n = 0; n < kEmbedMaxC; ++n) {
+        if (n < C0) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < kEmbedMaxK; ++k)
+                if (k < KP) acc = fmaf(in[k], sw[n * KP + k], acc);
+            y[n] = acc + sb[n];
+            s += y[n];
+        }
+    }
+    const float mean = s / (float)C0;
+    float q = 0.f;
+#pragma unroll
+    for (int n = 0; n < kEmbedMaxC; ++n)
+        if (n < C0) { const float dlt = y[n] - mean; q = fmaf(dlt, dlt, q); }
+    const float rstd = 1.0f / sqrtf(q / (float)C0 + eps);
+    float* o = tok + (b * H * W + (long long)h * W + wq) * ld;
+#pragma unroll
+    for (int n = 0; n < kEmbedMaxC; ++n)
+        if (n < C0) o[n] = (y[n] - mean) * rstd * sg[n] + sbe[n];
+}
+
+// ------------------------------------------------------------------------------------------------ output conv
+// PatchDeEmbed.de_proj2 (scale.py:70-71,79): 3x3 / pad 1 convolution C0 -> 2 over the channels-last pixel map
+// Y1 [B, F, T2, ld]; writes the spectrum frame-major Xf[b, t, c2*F + f] (what the inverse STFT reads).
+// Packed weight: wp[tap][c][2].
+static __global__ void conv3x3_out_kernel(const float* __restrict__ Y1, const int ld, const int C0, const int F,
+                                   const int T2, const float* __restrict__ wp, const float* __restrict__ bias,
+                                   float* __restrict__ Xf, const long long total) {
+    extern __shared__ float swc[];   // 9*C0*2
+    for (int i = threadIdx.x; i < 9 * C0 * 2; i += blockDim.x) swc[i] = wp[i];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int t = (int)(idx % T2);
+    const int f = (int)((idx / T2) % F);
+    const long long b = idx / ((long long)T2 * F);
+    float a0 = 0.f, a1 = 0.f;
+    const int C4 = C0 & ~3;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int ff = f + kh - 1;
+        if (ff < 0 || ff >= F) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int tt = t + kw - 1;
+            if (tt < 0 || tt >= T2) continue;
+            const float* p = Y1 + ((b * F + ff) * (long long)T2 + tt) * ld;
+            const float* wv = swc + (kh * 3 + kw) * C0 * 2;
+            for (int c = 0; c < C4; c += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
+                a0 = fmaf(v.x, wv[2 * c + 0], a0); a1 = fmaf(v.x, wv[2 * c + 1], a1);
+                a0 = fmaf(v.y, wv[2 * c + 2], a0); a1 = fmaf(v.y, wv[2 * c + 3], a1);
+                a0 = fmaf(v.z, wv[2 * c + 4], a0); a1 = fmaf(v.z, wv[2 * c + 5], a1);
+                a0 = fmaf(v.w, wv[2 * c + 6], a0); a1 = fmaf(v.w, wv[2 * c + 7], a1);
+            }
+            for (int c = C4; c < C0; ++c) {
+                const float v = __ldg(p + c);
+                a0 = fmaf(v, wv[2 * c], a0); a1 = fmaf(v, wv[2 * c + 1], a1);
+            }
+        }
+    }
+    float* o = Xf + (b * T2 + t) * (long long)(2 * F);
+    o[f] = a0 + __ldg(bias);
+    o[F + f] = a1 + __ldg(bias + 1);
+}
+
+// ------------------------------------------------------------------------------------------------ layout helpers
+// Batched 2-D transpose: in [B][R][Cc] -> out [B][Cc][R] (frame-major spectrum <-> [B,2,F,T] planes).
+static __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, const int R, const int Cc) {
+    __shared__ float tile[32][33];
+    const long long b = blockIdx.z;
+    const float* ip = in + b * (long long)R * Cc;
+    float* op = out + b * (long long)R * Cc;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) tile[i][threadIdx.x] = ip[(long long)r * Cc + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) op[(long long)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+// Row re-pitch: dst[r*ldd + c] = src[r*lds + c] for c < C (dense <-> padded token rows).
+static __global__ void repitch_kernel(const float* __restrict__ src, const int lds, float* __restrict__ dst, const int ldd,
+                               const int C, const long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long r = idx / C;
+    const int c = (int)(idx - r * C);
+    dst[r * ldd + c] = src[r * lds + c];
+}
+
+// Eval-mode VQ "losses" (codebook.py:71-73; quantization.py:69-72): per batch row, mean over (T, d) of
+// (table[code] - z_e)^2 summed over groups / groups, accumulated into loss[b].
+static __global__ void vq_loss_kernel(const float* __restrict__ ze, const int ldz, const float* __restrict__ tables,
+                               const long long* __restrict__ codes, const int S, const int s, const int T,
+                               const int d, const int groups, const int ncodes, float* __restrict__ loss) {
+    const int b = blockIdx.x;
+    float acc = 0.f;
+    const int n = groups * T * d;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int g = i / (T * d);
+        const int rem = i - g * T * d;
+        const int t = rem / d, dd = rem - t * d;
+        const long long c = codes[(((long long)b * S + s) * groups + g) * T + t];
+        const float diff = tables[((long long)g * ncodes + c) * d + dd] - ze[((long long)b * T + t) * ldz + g * d + dd];
+        acc = fmaf(diff, diff, acc);
+    }
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) loss[b] += v / ((float)T * d) / (float)groups;
+    }
+}
+
+}  // namespace escb

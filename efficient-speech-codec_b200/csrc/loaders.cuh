@@ -1,0 +1,374 @@
+// A-loaders (how a logical GEMM row is gathered from HBM) and epilogues (where outputs land) for gemm.cuh.
+// Each one replaces a permute/reshape/contiguous chain of the reference; the cited lines are the behaviour
+// restated as index arithmetic.
+#pragma once
+#include "gemm.cuh"
+
+namespace escb {
+
+// =============================================================================================== A loaders
+// Contract: init(m, M, row) fills the per-row context; valid(row) == false means the whole row is zero
+// (out-of-range row or a zero-padded token); load1(row,k) returns element k (< K); load4(row,k,K) returns
+// elements k..k+3 with those >= K zeroed (k % 4 == 0, k < K).
+
+// Dense rows X[m*ld + k].
+struct ARows {
+    const float* X;
+    int ld;
+    struct Row { const float* p; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p = (m < M) ? X + m * (long long)ld : nullptr;
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+};
+
+// Window partition of a [B,H,W,C] token map zero-padded to (Hp,Wp) and cyclically shifted by `shift`
+// (attention.py:137-153, 246-250).  Row m = ((b*nWh + wh)*nWw + ww)*16 + (i*4 + j) reads the token at
+// h = (4*wh + i + shift) % Hp, w = (4*ww + j + shift) % Wp; tokens in the padding are all-zero rows
+// (the reference pads AFTER norm1, so they bypass LayerNorm).
+struct WindowGeom {
+    int H, W, Hp, Wp, shift, nWw, nW;   // nW = (Hp/4)*(Wp/4)
+    __device__ __forceinline__ long long token(long long m) const {
+        const int t = (int)(m & 15);
+        const long long wi = m >> 4;
+        const int win = (int)(wi % nW);
+        const long long b = wi / nW;
+        const int wh = win / nWw, ww = win % nWw;
+        int h = wh * 4 + (t >> 2) + shift, w = ww * 4 + (t & 3) + shift;
+        if (h >= Hp) h -= Hp;
+        if (w >= Wp) w -= Wp;
+        if (h >= H || w >= W) return -1;
+        return (b * H + h) * (long long)W + w;
+    }
+};
+
+struct AWindow {
+    const float* X;
+    int ld;
+    WindowGeom g;
+    struct Row { const float* p; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p = nullptr;
+        if (m < M) {
+            const long long t = g.token(m);
+            if (t >= 0) r.p = X + t * (long long)ld;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+};
+
+// PatchMerge gather (scale.py:7-14,104-112): row m = (b, h2, w) is [ x[b,2*h2,w,:] ; x[b,2*h2+1,w,:] ], K = 2C.
+struct AMerge {
+    const float* X;
+    int ld, H, W, C;
+    struct Row { const float* p0; const float* p1; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p0 = r.p1 = nullptr;
+        if (m < M) {
+            const int H2 = H >> 1;
+            const int w = (int)(m % W);
+            const long long bh = m / W;
+            const int h2 = (int)(bh % H2);
+            const long long b = bh / H2;
+            r.p0 = X + ((b * H + 2 * h2) * (long long)W + w) * ld;
+            r.p1 = r.p0 + (long long)W * ld;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p0 != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const { return k < C ? __ldg(r.p0 + k) : __ldg(r.p1 + (k - C)); }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        if ((C & 3) == 0) return k < C ? ldg4(r.p0 + k) : ldg4(r.p1 + (k - C));
+        float4 v;
+        v.x = load1(r, k);
+        v.y = (k + 1 < K) ? load1(r, k + 1) : 0.f;
+        v.z = (k + 2 < K) ? load1(r, k + 2) : 0.f;
+        v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
+        return v;
+    }
+};
+
+// Product-VQ frame of the residual enc - dec (csrvq.py:15-17; quantization.py:400-409).  The reference's frame
+// vector is ordered (o, c, h); the packed down-projection weight is permuted to k' = (h, o, c) so that a frame
+// is H contiguous runs of 2C floats: x[b, h*W + 2t + o, c].  Requires ld == C.
+struct AFrame {
+    const float* E;
+    const float* D;     // may be null (stream 0 quantizes enc itself)
+    int Hq, W, C;
+    struct Row { long long base; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.base = -1;
+        if (m < M) {
+            const int T = W >> 1;
+            const int t = (int)(m % T);
+            const long long b = m / T;
+            r.base = (b * Hq * (long long)W + 2 * t) * C;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.base >= 0; }
+    __device__ __forceinline__ long long off(const Row& r, int k) const {
+        const int h = k / (2 * C);
+        return r.base + (long long)h * W * C + (k - h * 2 * C);
+    }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        const long long o = off(r, k);
+        return D ? __ldg(E + o) - __ldg(D + o) : __ldg(E + o);
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        const long long o = off(r, k);
+        float4 e = ldg4(E + o);
+        if (D) {
+            const float4 d = ldg4(D + o);
+            e.x -= d.x; e.y -= d.y; e.z -= d.z; e.w -= d.w;
+        }
+        return e;
+    }
+};
+
+// Rows of de-quantised codebook vectors [z_q0 ; z_q1 ; z_q2] gathered from the RAW tables by code
+// (codebook.py:45-55; quantization.py:124-136).  codes layout [B, S, 3, T] int64, this stream at index s.
+struct ACodes {
+    const long long* codes;
+    const float* tables;   // [3][K][d] raw
+    int S, s, T, d, ncodes;
+    struct Row { int c0, c1, c2; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.c0 = -1; r.c1 = r.c2 = 0;
+        if (m < M) {
+            const int t = (int)(m % T);
+            const long long b = m / T;
+            const long long* p = codes + ((b * S + s) * 3) * (long long)T + t;
+            r.c0 = (int)p[0]; r.c1 = (int)p[T]; r.c2 = (int)p[2 * (long long)T];
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.c0 >= 0; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        const int g = k / d, dd = k - g * d;
+        const int c = g == 0 ? r.c0 : (g == 1 ? r.c1 : r.c2);
+        return __ldg(tables + ((long long)g * ncodes + c) * d + dd);
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        float4 v;
+        v.x = load1(r, k);
+        v.y = (k + 1 < K) ? load1(r, k + 1) : 0.f;
+        v.z = (k + 2 < K) ? load1(r, k + 2) : 0.f;
+        v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
+        return v;
+    }
+};
+
+// im2col of the 5x5 / pad 2 convolution over channels-last tokens [B,H,W,ld] (scale.py:66-68,77).
+// k = tap*ldc + c with tap = kh*5 + kw and ldc the padded channel count (48): the packed weight uses the same order.
+struct AIm2col {
+    const float* X;
+    int ld, H, W, C;
+    struct Row { const float* p; int h, w; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p = nullptr; r.h = r.w = 0;
+        if (m < M) {
+            r.w = (int)(m % W);
+            r.h = (int)((m / W) % H);
+            r.p = X + m * (long long)ld;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        const float4 v = load4(r, k & ~3, 1 << 30);
+        const int j = k & 3;
+        return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        const int tap = k / ld, c = k - tap * ld;
+        const int dh = tap / 5 - 2, dw = tap % 5 - 2;
+        const int hh = r.h + dh, ww = r.w + dw;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) return zero4();
+        return mask4(ldg4(r.p + ((long long)dh * W + dw) * ld + c), c, C);
+    }
+};
+
+// STFT framing with centre/reflect padding (base.py:22-24,36 -> torch.stft): row m = (b, t), element k is
+// x[b, reflect(t*hop - win/2 + k)], k in [0, win).  (The window is applied by the packed DFT basis.)
+struct AStftFrames {
+    const float* X;
+    long long L;
+    int T, hop, half_win;
+    struct Row { const float* p; long long i0; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p = nullptr; r.i0 = 0;
+        if (m < M) {
+            const int t = (int)(m % T);
+            r.p = X + (m / T) * L;
+            r.i0 = (long long)t * hop - half_win;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        long long i = r.i0 + k;
+        if (i < 0) i = -i;
+        if (i >= L) i = 2 * (L - 1) - i;
+        return __ldg(r.p + i);
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        float4 v;
+        v.x = load1(r, k);
+        v.y = (k + 1 < K) ? load1(r, k + 1) : 0.f;
+        v.z = (k + 2 < K) ? load1(r, k + 2) : 0.f;
+        v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
+        return v;
+    }
+};
+
+// Inverse STFT as one GEMM (base.py:25-27,46-47 -> torch.istft): output chunk j (hop samples) sums the
+// `nov` = win/hop frames j-dt that overlap it: row m = (b, j), k = dt*F2 + cf reads Xf[b, j-dt, cf]
+// (frame-major spectrum, F2 = 2*in_freq); frames outside [0,T) contribute zero.
+struct AIstft {
+    const float* Xf;
+    int T, F2, j0, nchunks;
+    struct Row { const float* p; int j; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.p = nullptr; r.j = 0;
+        if (m < M) {
+            r.j = (int)(m % nchunks) + j0;
+            r.p = Xf + (m / nchunks) * (long long)T * F2;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        const int dt = k / F2, cf = k - dt * F2;
+        const int t = r.j - dt;
+        return (t >= 0 && t < T) ? __ldg(r.p + (long long)t * F2 + cf) : 0.f;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        const int dt = k / F2, cf = k - dt * F2;
+        const int t = r.j - dt;
+        return (t >= 0 && t < T) ? ldg4(r.p + (long long)t * F2 + cf) : zero4();
+    }
+};
+
+// =============================================================================================== epilogues
+// Contract: row(m, ctx) -> false skips the row; store(ctx, n, v) writes element n (< N).
+
+template <bool GELU, bool RES>
+struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
+    float* Y;
+    const float* bias;
+    const float* R;
+    int ldy, ldr;
+    struct Row { float* y; const float* r; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        c.y = Y + m * (long long)ldy;
+        c.r = RES ? R + m * (long long)ldr : nullptr;
+        return true;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        if (bias) v += __ldg(bias + n);
+        if (GELU) v = gelu_erf(v);
+        if (RES) v = c.r[n] + v;
+        c.y[n] = v;
+    }
+};
+
+// window reverse + reverse shift + crop + residual (attention.py:158-175): Y[token] = R[token] + (v + bias).
+struct EpiWindow {
+    float* Y;
+    const float* R;
+    const float* bias;
+    int ld;
+    WindowGeom g;
+    struct Row { long long off; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        const long long t = g.token(m);
+        c.off = t * (long long)ld;
+        return t >= 0;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        Y[c.off + n] = R[c.off + n] + (v + __ldg(bias + n));
+    }
+};
+
+// PatchSplit pixel shuffle (scale.py:16-23,142-144): row m = (b,h,w); n < Co goes to freq row 2h, the rest to 2h+1.
+struct EpiSplit {
+    float* Y;
+    int ldy, H, W, Co;
+    struct Row { float* y0; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        const int w = (int)(m % W);
+        const long long bh = m / W;     // b*H + h
+        c.y0 = Y + ((2 * bh) * (long long)W + w) * ldy;
+        return true;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        if (n < Co) c.y0[n] = v;
+        else c.y0[(long long)W * ldy + (n - Co)] = v;
+    }
+};
+
+// product-VQ post_process + post_fuse (quantization.py:411-432; csrvq.py:19-21): column n' = (h, o, c) of frame
+// (b, t) lands on token (h*W + 2t + o), channel c; out = v + dec.
+struct EpiFrame {
+    float* Y;
+    const float* D;   // may be null
+    int Hq, W, C;
+    struct Row { long long base; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        const int T = W >> 1;
+        const int t = (int)(m % T);
+        const long long b = m / T;
+        c.base = (b * Hq * (long long)W + 2 * t) * C;
+        return true;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        const int h = n / (2 * C);
+        const long long o = c.base + (long long)h * W * C + (n - h * 2 * C);
+        Y[o] = D ? v + D[o] : v;
+    }
+};
+
+// conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78):
+// n = (s1*pt + s2)*C + c -> pixel (pf*h + s1, pt*w + s2), channel c.
+struct EpiDeembed {
+    float* Y;
+    const float* bias;
+    int ldy, H, W, C, pf, pt;
+    struct Row { float* y; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        const int w = (int)(m % W);
+        const long long bh = m / W;
+        c.y = Y + ((bh * pf) * (long long)(W * pt) + (long long)w * pt) * ldy;
+        return true;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        const int s = n / C, ch = n - s * C;
+        const int s1 = s / pt, s2 = s - s1 * pt;
+        c.y[((long long)s1 * (W * pt) + s2) * ldy + ch] = v + __ldg(bias + n);
+    }
+};
+
+// overlap-add normalisation + trim of torch.istft: sample s = hop*(j - j0) + n of clip b gets v / envelope, where
+// the envelope is the sum of squared window taps of the frames that overlap it.
+struct EpiIstft {
+    float* Y;
+    const float* wsq;   // [win] squared window
+    int T, hop, nov, j0, nchunks;
+    long long out_len;
+    struct Row { float* y; int j; };
+    __device__ __forceinline__ bool row(long long m, Row& c) const {
+        const int jj = (int)(m % nchunks);
+        c.j = jj + j0;
+        c.y = Y + (m / nchunks) * out_len + (long long)jj * hop;
+        return true;
+    }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+        float env = 0.f;
+        for (int dt = 0; dt < nov; ++dt) {
+            const int t = c.j - dt;
+            if (t >= 0 && t < T) env += __ldg(wsq + dt * hop + n);
+        }
+        c.y[n] = v / env;
+    }
+};
+
+}  // namespace escb

@@ -1,0 +1,57 @@
+// Product-VQ ops of one stream.  Reference: quantization.py:74-136 (ProductVectorQuantize.encode/decode),
+// :388-432 (pre/post_process), codebook.py:20-55 (argmin / de-quantisation), csrvq.py:15-21,50-60 (fuse).
+#include "internal.h"
+#include "kernels.cuh"
+
+namespace escb {
+
+static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
+
+void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz) {
+    AFrame al{enc, dec, q.in_freq, W, q.in_dim};
+    EpiRows<false, false> ep{ze, nullptr, nullptr, ldz, 0};
+    const long long M = (long long)B * (W / 2);
+    L.note(GemmLauncher<false, AFrame, EpiRows<false, false>, 3, 6>::launch(L.st, al, noln(), q.down, M, ep));
+}
+
+void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
+               float* out) {
+    ACodes al{codes, q.raw, S, s, W / 2, q.d, q.ncodes};
+    EpiFrame ep{out, dec, q.in_freq, W, q.in_dim};
+    const long long M = (long long)B * (W / 2);
+    L.note(GemmLauncher<false, ACodes, EpiFrame, 8, 9>::launch(L.st, al, noln(), q.up, M, ep));
+}
+
+template <int D>
+static cudaError_t launch_argmin(cudaStream_t st, const QuantW& q, int g_first, int groups, const float* ze, int ldz,
+                                 long long rows, long long* out, int T, long long bstride) {
+    const int warps = 8;
+    const long long total = rows * groups;
+    const long long blocks = (total + warps - 1) / warps;
+    codebook_argmin_kernel<D><<<(unsigned)blocks, warps * 32, 0, st>>>(
+        ze, ldz, 0, q.d, q.cbn + (long long)g_first * q.ncodes * q.d, q.cnorm + (long long)g_first * q.ncodes,
+        q.ncodes, rows, out, T, bstride, groups, q.d);
+    return cudaGetLastError();
+}
+
+void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const float* ze, int ldz, long long rows,
+               long long* out, int T, long long bstride) {
+    cudaError_t e;
+    switch (q.d) {
+        case 6: e = launch_argmin<6>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        case 8: e = launch_argmin<8>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        case 12: e = launch_argmin<12>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        case 16: e = launch_argmin<16>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        case 32: e = launch_argmin<32>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        default: e = launch_argmin<0>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+    }
+    L.note(e);
+}
+
+void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
+                int T, float* loss) {
+    vq_loss_kernel<<<B, 256, 0, L.st>>>(ze, ldz, q.raw, codes, S, s, T, q.d, 3, q.ncodes, loss);
+    L.note(cudaGetLastError());
+}
+
+}  // namespace escb

@@ -1,0 +1,98 @@
+// Swin block ops: host launchers over gemm.cuh / kernels.cuh.  Reference: attention.py:129-178 (SwinBlock),
+// :215-244 (WindowAttention), :258-272 (FeedForward); scale.py:83-145 (PatchMerge / PatchSplit).
+#include "internal.h"
+#include "kernels.cuh"
+
+namespace escb {
+
+static inline LnParams lnp(const LnW& w) { return LnParams{w.g, w.b, kLnEps}; }
+static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
+
+void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq) {
+    AWindow al{x, ld, g};
+    EpiRows<false, false> ep{qkv, w.qkv.bias, nullptr, ldq, 0};
+    L.note(GemmLauncher<true, AWindow, EpiRows<false, false>, 7, 9>::launch(L.st, al, lnp(w.n1), w.qkv, M, ep));
+}
+
+void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
+             const WindowGeom& g, long long M) {
+    ARows al{att, lda};
+    EpiWindow ep{y, resid, w.proj.bias, ld, g};
+    L.note(GemmLauncher<false, ARows, EpiWindow, 3, 5, 6, 8, 9>::launch(L.st, al, noln(), w.proj, M, ep));
+}
+
+void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh) {
+    ARows al{x, ld};
+    EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
+    L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(w.n2), w.fc1, M, ep));
+}
+
+void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long M, float* x, int ld) {
+    ARows al{hid, ldh};
+    EpiRows<false, true> ep{x, w.fc2.bias, x, ld, ld};
+    L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(), w.fc2, M, ep));
+}
+
+void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {
+    AMerge al{x, ld, H, W, w.C};
+    EpiRows<false, false> ep{y, nullptr, nullptr, ldy, 0};
+    const long long M = (long long)B * (H / 2) * W;
+    L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(w.sn), w.sub, M, ep));
+}
+
+void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {
+    ARows al{x, ld};
+    EpiSplit ep{y, ldy, H, W, w.out_dim};
+    const long long M = (long long)B * H * W;
+    L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(w.sn), w.sub, M, ep));
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+template <int HD>
+static cudaError_t launch_attn(cudaStream_t st, const float* qkv, int ldq, float* att, int ldo, const float* relbias,
+                               int heads, int C, long long nwin, bool masked, const WindowGeom& g) {
+    int wpb = 256 / (16 * heads);
+    if (wpb < 1) wpb = 1;
+    while ((wpb * 16 * heads) % 32) ++wpb;
+    const int threads = wpb * 16 * heads;
+    if (threads > 1024) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)wpb * 16 * ldq * sizeof(float);
+    const float scale = (float)(1.0 / sqrt((double)HD));
+    const long long blocks = (nwin + wpb - 1) / wpb;
+    window_attn_kernel<HD><<<(unsigned)blocks, threads, smem, st>>>(qkv, ldq, att, ldo, relbias, heads, C, nwin, wpb,
+                                                                   scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp);
+    return cudaGetLastError();
+}
+
+#define ESCB_ATTN_HDS(X) X(4) X(6) X(8) X(12) X(15) X(16) X(24) X(32)
+
+void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
+                  int hd, int C, long long nwin, bool masked, const WindowGeom& g) {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (hd) {
+#define X(n) case n: e = launch_attn<n>(L.st, qkv, ldq, att, ldo, relbias, heads, C, nwin, masked, g); break;
+        ESCB_ATTN_HDS(X)
+#undef X
+        default: break;
+    }
+    L.note(e);
+}
+
+bool attention_supported(int hd) {
+    switch (hd) {
+#define X(n) case n: return true;
+        ESCB_ATTN_HDS(X)
+#undef X
+        default: return false;
+    }
+}
+
+cudaError_t swin_init() {
+    cudaError_t e = cudaSuccess;
+#define X(n) if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ESCB_ATTN_HDS(X)
+#undef X
+    return e;
+}
+
+}  // namespace escb

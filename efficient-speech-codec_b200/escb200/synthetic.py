@@ -20,7 +20,7 @@ from typing import Dict
 import numpy as np
 import torch
 
-from ..models.spec import CodecSpec, ManifestEntry, relative_position_index
+from .spec import CodecSpec, ManifestEntry, relative_position_index
 
 
 def _rs(key: str, seed: int) -> np.random.RandomState:

@@ -12,7 +12,7 @@ The reference imports two packages that are not installed here at module scope
 shimmed with the minimum surface before ``import esc``.  Nothing from the
 reference is copied into this repository: only its *outputs* on seeded inputs.
 
-Weights are the deterministic synthetic ones of ``escb200.utils.synthetic`` —
+Weights are the deterministic synthetic ones of ``escb200.synthetic`` —
 written over the reference model's own ``state_dict`` (``strict=True``), which
 also proves our key/shape manifest equals the reference's.
 """
@@ -62,8 +62,8 @@ def main():
     import esc as ref_esc
     assert ref_esc.__file__.startswith(REF), ref_esc.__file__
     import yaml
-    from escb200.models.spec import CodecSpec
-    from escb200.utils.synthetic import synth_state_dict, synth_audio
+    from escb200.spec import CodecSpec
+    from escb200.synthetic import synth_state_dict, synth_audio
 
     torch.manual_seed(0)
     torch.set_num_threads(8)

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from helpers import ADV, BASE, LARGE, i64, make_oracle
-from escb200.utils.synthetic import synth_audio
+from escb200.synthetic import synth_audio
 
 TOL = 2e-5
 
@@ -116,7 +116,7 @@ def test_pvq_layer_and_ties(golden):
 def test_manifest_equals_reference_state_dict():
     """Key / shape / dtype list of our spec == the reference ESC.state_dict() (captured by make_golden.py)."""
     import json, os
-    from escb200.models.spec import CodecSpec
+    from escb200.spec import CodecSpec
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_manifest.json")))
     for name, cfg in (("base", BASE), ("large", LARGE)):
         mine = [[e.key, list(e.shape), e.dtype] for e in CodecSpec.from_kwargs(**cfg).manifest()]
