@@ -64,6 +64,7 @@ struct escb_handle {
     QuantW quants[ESCB_MAX_LEVELS];
     FrontW front;
     std::atomic<long long> launches{0};
+    Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     // grow-only scratch for the *_host entry points
     std::mutex host_mu;
     void* host_scratch = nullptr;
@@ -592,6 +593,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.B = B;
     c.W = W;
     c.L.st = (cudaStream_t)stream;
+    c.L.prof = h->prof;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -971,9 +973,46 @@ int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, i
     Ctx c;
     c.h = h;
     c.L.st = (cudaStream_t)stream;
+    c.L.prof = h->prof;
     const QuantW& qw = h->quants[q];
     op_argmin(c.L, qw, g, 1, z, qw.d, rows, (long long*)idx, (int)std::min<int64_t>(rows, 1 << 30), 0);
     return finish(c, "escb_codebook_argmin");
+}
+
+static const char* const kOpNames[OP_COUNT] = {
+    "stft_gemm", "patch_embed", "qkv_gemm", "window_attention", "proj_gemm", "mlp1_gemm", "mlp2_gemm", "merge_gemm",
+    "split_gemm", "pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "vq_loss", "deembed_conv5x5_gemm",
+    "deembed_conv3x3", "istft_gemm", "layout"};
+
+int escb_profile_begin(escb_handle* h) {
+    if (!h) return fail(ESCB_EINVAL, "null handle");
+    if (h->prof) return fail(ESCB_ESTATE, "profiling is already active");
+    h->prof = new Profiler();
+    return ESCB_OK;
+}
+
+int escb_profile_end(escb_handle* h, escb_op_stat* stats, int32_t* n) {
+    if (!h || !stats || !n) return fail(ESCB_EINVAL, "null argument");
+    if (!h->prof) return fail(ESCB_ESTATE, "profiling is not active");
+    Profiler* p = h->prof;
+    h->prof = nullptr;
+    for (int i = 0; i < OP_COUNT; ++i) stats[i] = escb_op_stat{kOpNames[i], 0, 0.0, 0.0, 0.0};
+    const cudaError_t e = cudaDeviceSynchronize();
+    for (ProfRec& r : p->recs) {
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            stats[r.op].launches += 1;
+            stats[r.op].ms += ms;
+            stats[r.op].flops += r.flops;
+            stats[r.op].bytes += r.bytes;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    delete p;
+    *n = OP_COUNT;
+    if (e != cudaSuccess) return fail(ESCB_ECUDA, "escb_profile_end: %s", cudaGetErrorString(e));
+    return ESCB_OK;
 }
 
 int64_t escb_launch_count(const escb_handle* h) { return h ? (int64_t)h->launches.load() : 0; }

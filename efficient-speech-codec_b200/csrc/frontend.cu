@@ -8,6 +8,7 @@ namespace escb {
 static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
 
 void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long Ls, int T, float* Sf) {
+    L.begin(OP_STFT, 2.0 * B * T * f.win * 2 * f.F, 4.0 * (1.0 * B * Ls + 2.0 * B * T * f.F));
     AStftFrames al{audio, Ls, T, f.hop, f.win / 2};
     EpiRows<false, false> ep{Sf, nullptr, nullptr, 2 * f.F, 0};
     L.note(GemmLauncher<false, AStftFrames, EpiRows<false, false>, 8>::launch(L.st, al, noln(), f.dft, (long long)B * T, ep));
@@ -16,18 +17,21 @@ void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long 
 void op_patch_embed(Launcher& L, const FrontW& f, const float* Sf, int B, int T, int H, int W, float* tok, int ld) {
     const long long total = (long long)B * H * W;
     const int threads = 128;
+    L.begin(OP_EMBED, 2.0 * total * f.C0 * 2 * f.pf * f.pt, 4.0 * total * (2.0 * f.pf * f.pt + f.C0));
     patch_embed_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, L.st>>>(
         Sf, T, f.F, tok, ld, f.embed_w, f.embed_b, f.embed_ln.g, f.embed_ln.b, f.C0, f.pf, f.pt, H, W, total, kLnEps);
     L.note(cudaGetLastError());
 }
 
 void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, int H, int W, float* Y1, float* Xf) {
+    L.begin(OP_DEEMBED1, 2.0 * B * H * W * f.de1.N * 25 * f.C0, 4.0 * B * H * W * (f.C0 + f.de1.N));
     AIm2col al{tok, ld, H, W, f.C0};
     EpiDeembed ep{Y1, f.de1.bias, ld, H, W, f.C0, f.pf, f.pt};
     L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
     const int Fq = H * f.pf, T2 = W * f.pt;
     const long long total = (long long)B * Fq * T2;
     const int threads = 128;
+    L.begin(OP_DEEMBED2, 2.0 * total * 2 * 9 * f.C0, 4.0 * total * (f.C0 + 2.0));
     conv3x3_out_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 9 * f.C0 * 2 * sizeof(float), L.st>>>(
         Y1, ld, f.C0, Fq, T2, f.de2_w, f.de2_b, Xf, total);
     L.note(cudaGetLastError());
@@ -38,12 +42,14 @@ void op_istft(Launcher& L, const FrontW& f, const float* Xf, int B, int T, float
     const int n_fft = 2 * (f.F - 1);
     const int j0 = (n_fft / 2 - (n_fft - f.win) / 2) / f.hop;
     const int nchunks = T - 1;
+    L.begin(OP_ISTFT, 2.0 * B * nchunks * f.hop * f.nov * 2 * f.F, 4.0 * (2.0 * B * T * f.F + 1.0 * B * nchunks * f.hop));
     AIstft al{Xf, T, 2 * f.F, j0, nchunks};
     EpiIstft ep{audio, f.wsq, T, f.hop, f.nov, j0, nchunks, (long long)f.hop * (T - 1)};
     L.note(GemmLauncher<false, AIstft, EpiIstft, 5>::launch(L.st, al, noln(), f.idft, (long long)B * nchunks, ep));
 }
 
 void op_transpose(Launcher& L, const float* in, float* out, int B, int R, int C) {
+    L.begin(OP_LAYOUT, 0.0, 8.0 * B * R * C);
     dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
     transpose_kernel<<<grid, block, 0, L.st>>>(in, out, R, C);
     L.note(cudaGetLastError());
@@ -51,6 +57,7 @@ void op_transpose(Launcher& L, const float* in, float* out, int B, int R, int C)
 
 void op_repitch(Launcher& L, const float* src, int lds, float* dst, int ldd, int C, long long rows) {
     const long long total = rows * C;
+    L.begin(OP_LAYOUT, 0.0, 8.0 * total);
     repitch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.st>>>(src, lds, dst, ldd, C, total);
     L.note(cudaGetLastError());
 }

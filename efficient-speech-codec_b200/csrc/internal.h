@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/escb200.h"
 #include "gemm.cuh"
 #include "loaders.cuh"
@@ -45,11 +47,37 @@ struct FrontW {
     const float* de2_w; const float* de2_b;          // [9][C0][2], [2]
 };
 
+// Kernel classes for launch accounting / per-op timing (escb_profile_begin/end).
+enum OpId {
+    OP_STFT, OP_EMBED, OP_QKV, OP_ATTN, OP_PROJ, OP_MLP1, OP_MLP2, OP_MERGE, OP_SPLIT, OP_PVQ_DOWN, OP_ARGMIN,
+    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_COUNT
+};
+static_assert(OP_COUNT == ESCB_NUM_OPS, "escb200.h ESCB_NUM_OPS out of date");
+
+struct ProfRec { cudaEvent_t a, b; int op; double flops, bytes; };
+struct Profiler { std::vector<ProfRec> recs; };
+
 struct Launcher {                                    // stream + launch accounting + first-error latch
     cudaStream_t st = nullptr;
     long long launches = 0;
     cudaError_t err = cudaSuccess;
-    void note(cudaError_t e) { ++launches; if (err == cudaSuccess && e != cudaSuccess) err = e; }
+    Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
+    bool open = false;
+    // flops / bytes: ALGORITHMIC work of the launch that follows (true dims, no padding, no 3x anything)
+    void begin(int op, double flops, double bytes) {
+        if (!prof) return;
+        ProfRec r{nullptr, nullptr, op, flops, bytes};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        prof->recs.push_back(r);
+        open = true;
+    }
+    void note(cudaError_t e) {
+        ++launches;
+        if (err == cudaSuccess && e != cudaSuccess) err = e;
+        if (prof && open) { cudaEventRecord(prof->recs.back().b, st); open = false; }
+    }
 };
 
 constexpr float kLnEps = 1e-5f;

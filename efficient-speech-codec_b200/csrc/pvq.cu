@@ -11,6 +11,7 @@ void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* de
     AFrame al{enc, dec, q.in_freq, W, q.in_dim};
     EpiRows<false, false> ep{ze, nullptr, nullptr, ldz, 0};
     const long long M = (long long)B * (W / 2);
+    L.begin(OP_PVQ_DOWN, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim + 3.0 * q.d));
     L.note(GemmLauncher<false, AFrame, EpiRows<false, false>, 3, 6>::launch(L.st, al, noln(), q.down, M, ep));
 }
 
@@ -19,6 +20,7 @@ void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int 
     ACodes al{codes, q.raw, S, s, W / 2, q.d, q.ncodes};
     EpiFrame ep{out, dec, q.in_freq, W, q.in_dim};
     const long long M = (long long)B * (W / 2);
+    L.begin(OP_PVQ_UP, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim) + 24.0 * M);
     L.note(GemmLauncher<false, ACodes, EpiFrame, 8, 9>::launch(L.st, al, noln(), q.up, M, ep));
 }
 
@@ -36,6 +38,7 @@ static cudaError_t launch_argmin(cudaStream_t st, const QuantW& q, int g_first, 
 
 void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const float* ze, int ldz, long long rows,
                long long* out, int T, long long bstride) {
+    L.begin(OP_ARGMIN, 2.0 * rows * groups * q.ncodes * q.d, rows * groups * (4.0 * q.d + 8.0));
     cudaError_t e;
     switch (q.d) {
         case 6: e = launch_argmin<6>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
@@ -50,6 +53,7 @@ void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const floa
 
 void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
                 int T, float* loss) {
+    L.begin(OP_VQLOSS, 3.0 * B * T * 3 * q.d, 4.0 * B * T * 3 * q.d * 2);
     vq_loss_kernel<<<B, 256, 0, L.st>>>(ze, ldz, q.raw, codes, S, s, T, q.d, 3, q.ncodes, loss);
     L.note(cudaGetLastError());
 }

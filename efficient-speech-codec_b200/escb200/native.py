@@ -25,8 +25,9 @@ EXPORTS = [
     "escb_weight_numel", "escb_set_weight", "escb_finalize", "escb_time_patches", "escb_decoded_samples",
     "escb_workspace_bytes", "escb_encode", "escb_decode", "escb_forward", "escb_encode_host", "escb_decode_host",
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
-    "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count",
+    "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
 ]
+ESCB_NUM_OPS = 17
 
 
 class NativeLibraryMissing(ImportError):
@@ -48,6 +49,11 @@ class EscbConfig(C.Structure):
         ("overlap", C.c_int32), ("group_size", C.c_int32), ("codebook_size", C.c_int32),
         ("codebook_dims", C.c_int32 * ESCB_MAX_LEVELS), ("l2norm", C.c_int32),
     ]
+
+
+class EscbOpStat(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
 
 
 def library_path() -> str:
@@ -96,6 +102,8 @@ def lib() -> C.CDLL:
         "escb_pvq_decode": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, sz, vp]),
         "escb_codebook_argmin": (C.c_int, [vp, i32, i32, vp, i64, vp, vp]),
         "escb_launch_count": (i64, [vp]),
+        "escb_profile_begin": (C.c_int, [vp]),
+        "escb_profile_end": (C.c_int, [vp, C.POINTER(EscbOpStat), C.POINTER(i32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -190,6 +198,17 @@ class Handle:
 
     def launch_count(self) -> int:
         return self._lib.escb_launch_count(self._h)
+
+    def profile_begin(self) -> None:
+        check(self._lib.escb_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        """{op name: dict(launches, ms, flops, bytes)} accumulated since profile_begin()."""
+        stats = (EscbOpStat * ESCB_NUM_OPS)()
+        n = C.c_int32()
+        check(self._lib.escb_profile_end(self._h, stats, C.byref(n)))
+        return {stats[i].name.decode(): dict(launches=stats[i].launches, ms=stats[i].ms, flops=stats[i].flops,
+                                             bytes=stats[i].bytes) for i in range(n.value)}
 
 
 def ptr(t: Optional["object"]) -> C.c_void_p:

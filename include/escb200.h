@@ -37,6 +37,7 @@ extern "C" {
 #define ESCB_ABI_VERSION 1
 #define ESCB_MAX_LEVELS 8
 #define ESCB_MAX_DEPTH 8
+#define ESCB_NUM_OPS 17
 
 enum {
     ESCB_OK = 0,
@@ -175,6 +176,20 @@ ESCB_API int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes_dev
  *   z_dev [rows, codebook_dim_q] (already down-projected) -> idx_dev [rows] int64. */
 ESCB_API int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z_dev, int64_t rows, int64_t* idx_dev,
                          void* stream);
+
+/* Per-kernel-class timing (bench.py's roofline figures).  Between escb_profile_begin and escb_profile_end every
+ * kernel launched for this handle is bracketed by CUDA events on its stream; escb_profile_end synchronises the
+ * device and returns, per class, the launch count, the summed device time and the summed ALGORITHMIC flops /
+ * bytes (true dims, no padding).  Debug facility: not thread-safe, not for use inside a timed throughput run. */
+typedef struct escb_op_stat {
+    const char* name;
+    int64_t launches;
+    double ms;
+    double flops;
+    double bytes;
+} escb_op_stat;
+ESCB_API int escb_profile_begin(escb_handle* h);
+ESCB_API int escb_profile_end(escb_handle* h, escb_op_stat* stats /* [ESCB_NUM_OPS] */, int32_t* n);
 
 /* Number of kernels the library has launched on behalf of this handle since creation (bench.py's gpu_launches). */
 ESCB_API int64_t escb_launch_count(const escb_handle* h);
