@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,6 +65,7 @@ struct escb_handle {
     QuantW quants[ESCB_MAX_LEVELS];
     FrontW front;
     std::atomic<long long> launches{0};
+    bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     // grow-only scratch for the *_host entry points
     std::mutex host_mu;
@@ -209,8 +211,47 @@ struct Packer {
         for (int n = 0; n < N; ++n)
             for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W.host[(size_t)n * K + k];
         put(&gw.wt, t);
+        put_tc(gw, t);
         gw.bias = nullptr;
         if (bname) put(&gw.bias, w(bname));
+    }
+    static float tf32_rna(float x) {           // cvt.rna.tf32.f32: nearest, ties away, 10 mantissa bits kept
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
+        u &= 0xffffe000u;
+        memcpy(&x, &u, 4);
+        return x;
+    }
+    // tcgen05 operand images from the packed Wt [Kpad][ldw] (see TcWeight in gemm.cuh)
+    void put_tc(GemmWeight& gw, const std::vector<float>& t) {
+        TcWeight& w = gw.tc;
+        w.N = gw.N;
+        w.K = gw.K;
+        w.ntn = (gw.N + tc::MAX_BN - 1) / tc::MAX_BN;
+        w.BN = round_up((gw.N + w.ntn - 1) / w.ntn, 16);
+        w.nkb = (gw.K + tc::KB - 1) / tc::KB;
+        const size_t img = (size_t)w.BN * 32;                 // floats per image
+        std::vector<float> out((size_t)w.ntn * w.nkb * 2 * img, 0.f);
+        for (int nt = 0; nt < w.ntn; ++nt)
+            for (int kb = 0; kb < w.nkb; ++kb) {
+                float* hi = out.data() + ((size_t)nt * w.nkb + kb) * 2 * img;
+                float* lo = hi + img;
+                for (int r = 0; r < w.BN; ++r) {
+                    const int n = nt * w.BN + r;
+                    if (n >= gw.N) continue;
+                    for (int kk = 0; kk < 32; ++kk) {
+                        const int k = kb * 32 + kk;
+                        if (k >= gw.K) break;
+                        const float v = t[(size_t)k * gw.ldw + n];
+                        const float h = tf32_rna(v);
+                        const size_t pos = (size_t)r * 32 + (size_t)(((kk >> 2) ^ (r & 7)) << 2) + (kk & 3);
+                        hi[pos] = h;
+                        lo[pos] = tf32_rna(v - h);
+                    }
+                }
+            }
+        put(&w.img, out);
     }
     static void init_gemm(GemmWeight& gw, int N, int K, std::vector<float>& t) {
         gw.N = N;
@@ -218,6 +259,7 @@ struct Packer {
         gw.Kpad = round_up(K, kBK);
         gw.ldw = round_up(N, 4);
         gw.bias = nullptr;
+        gw.tc = TcWeight{nullptr, N, K, 0, 0, 0};
         t.assign((size_t)gw.Kpad * gw.ldw, 0.f);
     }
 };
@@ -370,6 +412,7 @@ static void pack_front(Packer& P) {
             for (int tap = 0; tap < 25; ++tap)
                 de1[(size_t)(tap * ld0 + c) * f.de1.ldw + n] = w1[((size_t)n * C0 + c) * 25 + tap];
     P.put(&f.de1.wt, de1);
+    P.put_tc(f.de1, de1);
     P.put(&f.de1.bias, P.w("decoder.patch_deembed.de_proj1.bias"));
     // de_proj2 (scale.py:70-71): wp[tap][c][2]
     const std::vector<float>& w2 = P.w("decoder.patch_deembed.de_proj2.weight");
@@ -594,6 +637,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.W = W;
     c.L.st = (cudaStream_t)stream;
     c.L.prof = h->prof;
+    c.L.tc = h->use_tc;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -648,6 +692,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     }
     escb_handle* h = new escb_handle();
     h->cfg = c;
+    if (const char* e = getenv("ESCB_GEMM")) h->use_tc = strcmp(e, "simt") != 0;
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
     h->F = c.in_freq; h->n_fft = n_fft; h->win = c.win_length; h->hop = c.hop_length;

@@ -27,7 +27,8 @@ void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, i
     L.begin(OP_DEEMBED1, 2.0 * B * H * W * f.de1.N * 25 * f.C0, 4.0 * B * H * W * (f.C0 + f.de1.N));
     AIm2col al{tok, ld, H, W, f.C0};
     EpiDeembed ep{Y1, f.de1.bias, ld, H, W, f.C0, f.pf, f.pt};
-    L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
+    if (L.tc) L.note(tc::launch<false, AIm2col, EpiDeembed>(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
+    else L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
     const int Fq = H * f.pf, T2 = W * f.pt;
     const long long total = (long long)B * Fq * T2;
     const int threads = 128;

@@ -187,10 +187,19 @@ gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const 
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+// Operand images for the tcgen05 engine (tc_gemm.cuh): per (n tile, 32-wide K block) one contiguous chunk
+// [hi image | lo image], each BN rows x 128 bytes in the 128-byte-swizzled K-major layout, hi = tf32(w),
+// lo = tf32(w - hi).  img == nullptr: this weight has no tensor-core image.
+struct TcWeight {
+    const float* img;
+    int N, K, BN, ntn, nkb;
+};
+
 struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be null
     const float* wt;
     const float* bias;
     int N, K, Kpad, ldw;
+    TcWeight tc;
 };
 
 inline int pick_tn(int N) {

@@ -8,6 +8,7 @@
 #include "../../include/escb200.h"
 #include "gemm.cuh"
 #include "loaders.cuh"
+#include "tc_gemm.cuh"
 
 namespace escb {
 
@@ -61,6 +62,7 @@ struct Launcher {                                    // stream + launch accounti
     cudaStream_t st = nullptr;
     long long launches = 0;
     cudaError_t err = cudaSuccess;
+    bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     bool open = false;
     // flops / bytes: ALGORITHMIC work of the launch that follows (true dims, no padding, no 3x anything)

@@ -269,6 +269,15 @@ struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
         if (RES) v = c.r[n] + v;
         c.y[n] = v;
     }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {   // n % 4 == 0, ldy % 4 == 0
+        if (bias) { const float4 b = ldg4(bias + n); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (RES) {
+            const float4 r = *reinterpret_cast<const float4*>(c.r + n);
+            v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+        }
+        *reinterpret_cast<float4*>(c.y + n) = v;
+    }
 };
 
 // window reverse + reverse shift + crop + residual (attention.py:158-175): Y[token] = R[token] + (v + bias).
@@ -287,6 +296,12 @@ struct EpiWindow {
     __device__ __forceinline__ void store(const Row& c, int n, float v) const {
         Y[c.off + n] = R[c.off + n] + (v + __ldg(bias + n));
     }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
+        const float4 b = ldg4(bias + n);
+        const float4 r = *reinterpret_cast<const float4*>(R + c.off + n);
+        v.x = r.x + (v.x + b.x); v.y = r.y + (v.y + b.y); v.z = r.z + (v.z + b.z); v.w = r.w + (v.w + b.w);
+        *reinterpret_cast<float4*>(Y + c.off + n) = v;
+    }
 };
 
 // PatchSplit pixel shuffle (scale.py:16-23,142-144): row m = (b,h,w); n < Co goes to freq row 2h, the rest to 2h+1.
@@ -303,6 +318,14 @@ struct EpiSplit {
     __device__ __forceinline__ void store(const Row& c, int n, float v) const {
         if (n < Co) c.y0[n] = v;
         else c.y0[(long long)W * ldy + (n - Co)] = v;
+    }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
+        if ((Co & 3) == 0) {
+            float* p = n < Co ? c.y0 + n : c.y0 + (long long)W * ldy + (n - Co);
+            *reinterpret_cast<float4*>(p) = v;
+        } else {
+            store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
+        }
     }
 };
 
@@ -325,6 +348,12 @@ struct EpiFrame {
         const long long o = c.base + (long long)h * W * C + (n - h * 2 * C);
         Y[o] = D ? v + D[o] : v;
     }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {   // 2C % 4 == 0
+        const int h = n / (2 * C);
+        const long long o = c.base + (long long)h * W * C + (n - h * 2 * C);
+        if (D) { const float4 d = *reinterpret_cast<const float4*>(D + o); v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w; }
+        *reinterpret_cast<float4*>(Y + o) = v;
+    }
 };
 
 // conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78):
@@ -344,6 +373,9 @@ struct EpiDeembed {
         const int s = n / C, ch = n - s * C;
         const int s1 = s / pt, s2 = s - s1 * pt;
         c.y[((long long)s1 * (W * pt) + s2) * ldy + ch] = v + __ldg(bias + n);
+    }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
+        store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
     }
 };
 
@@ -368,6 +400,9 @@ struct EpiIstft {
             if (t >= 0 && t < T) env += __ldg(wsq + dt * hop + n);
         }
         c.y[n] = v / env;
+    }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
+        store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
     }
 };
 
