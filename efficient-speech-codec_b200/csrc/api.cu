@@ -24,6 +24,7 @@
 
 namespace escb {
 bool attention_supported(int hd);
+bool argmin_supported(int d);
 
 static thread_local std::string g_err;
 
@@ -335,7 +336,7 @@ static void pack_quant(Packer& P, int q) {
     P.put(&qw.down.wt, down);
     P.put(&qw.up.wt, up);
     // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
-    std::vector<float> raw((size_t)3 * K * dd), cbn((size_t)3 * K * dd), cn((size_t)3 * K);
+    std::vector<float> raw((size_t)3 * K * dd), cbt((size_t)3 * K * dd), cn((size_t)3 * K);
     for (int g = 0; g < 3; ++g) {
         const std::vector<float>& e = P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight");
         for (int c = 0; c < K; ++c) {
@@ -347,14 +348,14 @@ static void pack_quant(Packer& P, int q) {
                 const float v = e[(size_t)c * dd + j];
                 const float nv = v / den;
                 raw[((size_t)g * K + c) * dd + j] = v;
-                cbn[((size_t)g * K + c) * dd + j] = nv;
+                cbt[((size_t)g * dd + j) * K + c] = nv;
                 s2 = fmaf(nv, nv, s2);
             }
             cn[(size_t)g * K + c] = s2;
         }
     }
     P.put(&qw.raw, raw);
-    P.put(&qw.cbn, cbn);
+    P.put(&qw.cbt, cbt);
     P.put(&qw.cnorm, cn);
 }
 
@@ -683,7 +684,9 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
         if (c.h_dims[l] < 1) return fail(ESCB_EINVAL, "h_dims[%d] must be positive", l);
         if (l < c.num_levels - 1 && (top >> l) % 2) return fail(ESCB_EINVAL, "odd frequency-patch counts are not supported");
         if (l > 0 && (c.h_dims[l] & 3)) return fail(ESCB_EINVAL, "h_dims[%d] must be a multiple of 4", l);
-        if (c.codebook_dims[l] < 1 || c.codebook_dims[l] > 64) return fail(ESCB_EINVAL, "codebook_dims[%d] must be in [1, 64]", l);
+        if (!argmin_supported(c.codebook_dims[l]))
+            return fail(ESCB_EINVAL, "codebook_dims[%d]=%d has no argmin kernel (6, 8, 12, 16, 24, 32)", l, c.codebook_dims[l]);
+        if (c.codebook_size % 4) return fail(ESCB_EINVAL, "codebook_size must be a multiple of 4");
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {

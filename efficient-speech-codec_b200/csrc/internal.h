@@ -34,7 +34,7 @@ struct QuantW {
     GemmWeight down;                                 // K = frame_dim in (h,o,c) order, N = 3d (block structured)
     GemmWeight up;                                   // K = 3d, N = frame_dim in (h,o,c) order
     const float* raw;                                // [3][ncodes][d]
-    const float* cbn;                                // [3][ncodes][d] L2-normalised
+    const float* cbt;                                // [3][d][ncodes] L2-normalised, transposed
     const float* cnorm;                              // [3][ncodes] squared norms of cbn rows
 };
 

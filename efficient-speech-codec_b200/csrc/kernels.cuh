@@ -89,57 +89,128 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const int ldq,
 
 // ------------------------------------------------------------------------------------------------ RVQ argmin
 // Codebook.quantize_to_code (codebook.py:20-43): z and the table are L2-normalised (x / max(|x|, 1e-12)), the
-// distance is (|z|^2 - (2z).c) + |c|^2 and the FIRST minimum wins.  cbn / cnorm are the normalised table and its
-// squared norms, precomputed once per weight load.  One warp per (row, group): each lane scans 1/32 of the codes in
-// increasing order (strict <), then a lexicographic (dist, index) warp reduction keeps the lowest index on ties.
-// codes are written straight into the [B, S, G, T] tensor.
+// distance is (|z|^2 - (2z).c) + |c|^2 and the FIRST minimum wins.  cbt / cnorm are the normalised table
+// (transposed to [group][d][code]) and its squared norms, precomputed once per weight load.
+//
+// One block = 32 rows x all codes of one group.  The codebook streams through shared memory in chunks of 256
+// codes; each thread keeps an 8-row x 4-code register tile, so one k step is 3 LDS.128 for 32 FFMA (the naive
+// one-warp-per-row scan was LDS/LDG bound at 0.8 TFLOP/s).  Every dot product is still the same sequential
+// k = 0..d-1 FMA chain, each thread scans its codes in increasing order with a strict <, and the final
+// lexicographic (dist, index) reduction keeps the lowest index on ties.  Codes land in the [B, S, G, T] tensor.
+constexpr int kArgminRows = 32;
+constexpr int kArgminChunk = 256;
 template <int D>
-__global__ void codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int zoff, const int d_rt,
-                                       const float* __restrict__ cbn, const float* __restrict__ cnorm,
-                                       const int ncodes, const long long rows, long long* __restrict__ out,
-                                       const int T, const long long bstride, const int groups, const int d_stride) {
-    const int lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= rows * groups) return;
-    const long long m = wid / groups;
-    const int g = (int)(wid - m * groups);
-    const int d = D > 0 ? D : d_rt;
-    constexpr int DM = D > 0 ? D : 64;
-    const float* zp = z + m * (long long)ldz + zoff + g * d_stride;
-    float zn[DM];
-    float ss = 0.f;
+__global__ void __launch_bounds__(256)
+codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int d_stride, const float* __restrict__ cbt,
+                       const float* __restrict__ cnorm, const int ncodes, const long long rows,
+                       long long* __restrict__ out, const int T, const long long bstride) {
+    __shared__ __align__(16) float zs[D][kArgminRows];        // 2 * z_hat, transposed
+    __shared__ float zzs[kArgminRows];
+    __shared__ __align__(16) float cbs[D][kArgminChunk];
+    __shared__ float cns[kArgminChunk];
+    __shared__ float redv[kArgminRows][2];
+    __shared__ int redi[kArgminRows][2];
+    const int tid = threadIdx.x, g = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * kArgminRows;
+    if (tid < kArgminRows) {
+        const long long m = row0 + tid;
+        float zn[D];
+        float ss = 0.f;
+        if (m < rows) {
+            const float* zp = z + m * (long long)ldz + g * d_stride;
 #pragma unroll
-    for (int k = 0; k < DM; ++k)
-        if (k < d) { zn[k] = __ldg(zp + k); ss = fmaf(zn[k], zn[k], ss); }
-    const float denom = fmaxf(sqrtf(ss), 1e-12f);
-    float zz = 0.f;
+            for (int k = 0; k < D; ++k) { zn[k] = __ldg(zp + k); ss = fmaf(zn[k], zn[k], ss); }
+        } else {
 #pragma unroll
-    for (int k = 0; k < DM; ++k)
-        if (k < d) { zn[k] = zn[k] / denom; zz = fmaf(zn[k], zn[k], zz); zn[k] = 2.0f * zn[k]; }
-    const float* cb = cbn + (long long)g * ncodes * d;
+            for (int k = 0; k < D; ++k) zn[k] = 0.f;
+        }
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+        float zz = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float v = zn[k] / denom;
+            zz = fmaf(v, v, zz);
+            zs[k][tid] = 2.0f * v;
+        }
+        zzs[tid] = zz;
+    }
+    const int cg = tid & 63, rg = tid >> 6;                   // codes cg*4..+3 of the chunk, rows rg*8..+7
+    float best[8];
+    int besti[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { best[r] = 3.0e38f; besti[r] = 0x7fffffff; }
+    const float* cb = cbt + (long long)g * D * ncodes;
     const float* cn = cnorm + (long long)g * ncodes;
-    float best = 3.0e38f;
-    int besti = 0x7fffffff;
-    for (int c = lane; c < ncodes; c += 32) {
-        const float* cp = cb + (long long)c * d;
-        float dot = 0.f;
+    for (int chunk = 0; chunk < ncodes; chunk += kArgminChunk) {
+        __syncthreads();
+        for (int i = tid; i < D * (kArgminChunk / 4); i += 256) {
+            const int k = i / (kArgminChunk / 4), c4 = (i % (kArgminChunk / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chunk + c4 + 3 < ncodes) v = __ldg(reinterpret_cast<const float4*>(cb + (long long)k * ncodes + chunk + c4));
+            else {
+                if (chunk + c4 + 0 < ncodes) v.x = __ldg(cb + (long long)k * ncodes + chunk + c4 + 0);
+                if (chunk + c4 + 1 < ncodes) v.y = __ldg(cb + (long long)k * ncodes + chunk + c4 + 1);
+                if (chunk + c4 + 2 < ncodes) v.z = __ldg(cb + (long long)k * ncodes + chunk + c4 + 2);
+            }
+            *reinterpret_cast<float4*>(&cbs[k][c4]) = v;
+        }
+        cns[tid] = (chunk + tid < ncodes) ? __ldg(cn + chunk + tid) : 3.0e38f;
+        __syncthreads();
+        float acc[8][4];
 #pragma unroll
-        for (int k = 0; k < DM; ++k)
-            if (k < d) dot = fmaf(zn[k], __ldg(cp + k), dot);
-        const float dist = (zz - dot) + __ldg(cn + c);
-        if (dist < best) { best = dist; besti = c; }
-    }
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float4 c = *reinterpret_cast<const float4*>(&cbs[k][cg * 4]);
+            const float4 z0 = *reinterpret_cast<const float4*>(&zs[k][rg * 8]);
+            const float4 z1 = *reinterpret_cast<const float4*>(&zs[k][rg * 8 + 4]);
+            const float zr[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            const float cj[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(zr[r], cj[j], acc[r][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int code = chunk + cg * 4 + j;
+            const float cnj = cns[cg * 4 + j];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float dist = (zzs[rg * 8 + r] - acc[r][j]) + cnj;
+                if (dist < best[r]) { best[r] = dist; besti[r] = code; }
+            }
+        }
     }
-    if (lane == 0) {
-        if (besti == 0x7fffffff) besti = 0;       // all-NaN row: torch.min returns index 0 of the NaN run start
-        const long long b = m / T;
-        const int t = (int)(m - b * T);
-        out[b * bstride + (long long)g * T + t] = besti;
+    const int lane = tid & 31, wsel = (tid >> 5) & 1;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        float bv = best[r];
+        int bi = besti[r];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { redv[rg * 8 + r][wsel] = bv; redi[rg * 8 + r][wsel] = bi; }
+    }
+    __syncthreads();
+    if (tid < kArgminRows) {
+        const long long m = row0 + tid;
+        if (m < rows) {
+            float bv = redv[tid][0];
+            int bi = redi[tid][0];
+            const float ov = redv[tid][1];
+            const int oi = redi[tid][1];
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            if (bi == 0x7fffffff) bi = 0;                     // all-NaN row
+            const long long b = m / T;
+            const int t = (int)(m - b * T);
+            out[b * bstride + (long long)g * T + t] = bi;
+        }
     }
 }
 

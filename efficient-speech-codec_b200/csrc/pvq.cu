@@ -27,26 +27,27 @@ void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int 
 template <int D>
 static cudaError_t launch_argmin(cudaStream_t st, const QuantW& q, int g_first, int groups, const float* ze, int ldz,
                                  long long rows, long long* out, int T, long long bstride) {
-    const int warps = 8;
-    const long long total = rows * groups;
-    const long long blocks = (total + warps - 1) / warps;
-    codebook_argmin_kernel<D><<<(unsigned)blocks, warps * 32, 0, st>>>(
-        ze, ldz, 0, q.d, q.cbn + (long long)g_first * q.ncodes * q.d, q.cnorm + (long long)g_first * q.ncodes,
-        q.ncodes, rows, out, T, bstride, groups, q.d);
+    dim3 grid((unsigned)((rows + kArgminRows - 1) / kArgminRows), (unsigned)groups);
+    codebook_argmin_kernel<D><<<grid, 256, 0, st>>>(ze, ldz, q.d, q.cbt + (long long)g_first * q.ncodes * q.d,
+                                                    q.cnorm + (long long)g_first * q.ncodes, q.ncodes, rows, out, T,
+                                                    bstride);
     return cudaGetLastError();
 }
+
+bool argmin_supported(int d) { return d == 6 || d == 8 || d == 12 || d == 16 || d == 24 || d == 32; }
 
 void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const float* ze, int ldz, long long rows,
                long long* out, int T, long long bstride) {
     L.begin(OP_ARGMIN, 2.0 * rows * groups * q.ncodes * q.d, rows * groups * (4.0 * q.d + 8.0));
-    cudaError_t e;
+    cudaError_t e = cudaErrorInvalidValue;
     switch (q.d) {
         case 6: e = launch_argmin<6>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
         case 8: e = launch_argmin<8>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
         case 12: e = launch_argmin<12>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
         case 16: e = launch_argmin<16>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        case 24: e = launch_argmin<24>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
         case 32: e = launch_argmin<32>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
-        default: e = launch_argmin<0>(L.st, q, g_first, groups, ze, ldz, rows, out, T, bstride); break;
+        default: break;
     }
     L.note(e);
 }

@@ -120,7 +120,6 @@ __global__ void __launch_bounds__(THREADS, 2)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ typename AL::Row rows[BM];
-    __shared__ float2 stats[LN ? BM : 1];
     __shared__ __align__(8) uint64_t bars[3];          // [0],[1]: B stage landed; [2]: MMAs of a K block retired
     __shared__ uint32_t tmem_slot;
 
@@ -154,44 +153,62 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         }
     }
 
-    if (LN) {   // per-row mean / rstd, two passes, one warp per row (second pass hits L1)
-        for (int i = 0; i < BM / (THREADS / 32); ++i) {
-            const int r = warp * (BM / (THREADS / 32)) + i;
-            const typename AL::Row row = rows[r];
-            float mean = 0.f, rstd = 0.f;
-            if (al.valid(row)) {
-                float s = 0.f;
-                for (int k = lane * 4; k < K; k += 128) { const float4 v = al.load4(row, k, K); s += (v.x + v.y) + (v.z + v.w); }
+    // A producer mapping: 16-byte chunk c of the 128-byte row, rows r0 + 32 i (8 consecutive lanes share a row)
+    const int c = tid & 7, r0 = tid >> 3;
+    typename AL::Row myrow[4];
+    bool vld[4];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                mean = s / (float)K;
-                float q = 0.f;
-                for (int k = lane * 4; k < K; k += 128) {
-                    const float4 v = al.load4(row, k, K);
-                    float d = v.x - mean; q = fmaf(d, d, q);
-                    if (k + 1 < K) { d = v.y - mean; q = fmaf(d, d, q); }
-                    if (k + 2 < K) { d = v.z - mean; q = fmaf(d, d, q); }
-                    if (k + 3 < K) { d = v.w - mean; q = fmaf(d, d, q); }
-                }
+    for (int i = 0; i < 4; ++i) { myrow[i] = rows[r0 + 32 * i]; vld[i] = al.valid(myrow[i]); }
+
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {0.f, 0.f, 0.f, 0.f};
+    if (LN) {   // per-row mean / rstd, two passes; every load of a pass is independent (second pass hits L1/L2)
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int k = kb * KB + c * 4;
+            if (k < K) {
 #pragma unroll
-                for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                rstd = 1.0f / sqrtf(q / (float)K + ln.eps);
+                for (int i = 0; i < 4; ++i)
+                    if (vld[i]) { const float4 v = al.load4(myrow[i], k, K); s[i] += (v.x + v.y) + (v.z + v.w); }
             }
-            if (lane == 0) stats[r] = make_float2(mean, rstd);
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 4);
+            mean[i] = s[i] / (float)K;
+            s[i] = 0.f;
+        }
+#pragma unroll 4
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int k = kb * KB + c * 4;
+            if (k < K) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (vld[i]) {
+                        const float4 v = al.load4(myrow[i], k, K);
+                        float d = v.x - mean[i]; s[i] = fmaf(d, d, s[i]);
+                        if (k + 1 < K) { d = v.y - mean[i]; s[i] = fmaf(d, d, s[i]); }
+                        if (k + 2 < K) { d = v.z - mean[i]; s[i] = fmaf(d, d, s[i]); }
+                        if (k + 3 < K) { d = v.w - mean[i]; s[i] = fmaf(d, d, s[i]); }
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 4);
+            rstd[i] = 1.0f / sqrtf(s[i] / (float)K + ln.eps);
+        }
     }
 
-    // A producer mapping: 16-byte chunk c of the 128-byte row, rows r0 + 32 i
-    const int c = tid & 7, r0 = tid >> 3;
     float4 a[4];
     auto load_a = [&](int kb) {
         const int k = kb * KB + c * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const typename AL::Row row = rows[r0 + 32 * i];
-            a[i] = (al.valid(row) && k < K) ? al.load4(row, k, K) : zero4();
-        }
+        for (int i = 0; i < 4; ++i) a[i] = (vld[i] && k < K) ? al.load4(myrow[i], k, K) : zero4();
     };
     load_a(0);
 
@@ -204,12 +221,11 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         for (int i = 0; i < 4; ++i) {
             const int r = r0 + 32 * i;
             float4 v = a[i];
-            if (LN && k < K && al.valid(rows[r])) {
-                const float2 st = stats[r];
-                v.x = (v.x - st.x) * st.y * g.x + be.x;
-                v.y = (v.y - st.x) * st.y * g.y + be.y;
-                v.z = (v.z - st.x) * st.y * g.z + be.z;
-                v.w = (v.w - st.x) * st.y * g.w + be.w;
+            if (LN && k < K && vld[i]) {
+                v.x = (v.x - mean[i]) * rstd[i] * g.x + be.x;
+                v.y = (v.y - mean[i]) * rstd[i] * g.y + be.y;
+                v.z = (v.z - mean[i]) * rstd[i] * g.z + be.z;
+                v.w = (v.w - mean[i]) * rstd[i] * g.w + be.w;
                 v = mask4(v, k, K);
             }
             float4 hi, lo;
