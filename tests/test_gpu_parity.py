@@ -265,3 +265,32 @@ def test_native_library_is_what_ran(base0):
     n0 = h.launch_count()
     base0.encode(synth_audio(1, 16000, seed=1).cuda(), 6)
     assert h.launch_count() > n0
+
+
+def test_compress_script_plumbing(tmp_path):
+    """BASELINE config 1: scripts.compress on one 3 s wav + checkpoint folder, outputs equal the oracle's."""
+    import yaml
+    from scripts import compress
+    from scripts.utils import load_wav, save_wav
+    from escb200.spec import CodecSpec
+    from escb200.synthetic import synth_state_dict
+    sd = synth_state_dict(CodecSpec.from_kwargs(**BASE), 0)
+    mdir = tmp_path / "esc9kbps"
+    mdir.mkdir()
+    torch.save({"model_state_dict": sd}, mdir / "model.pth")
+    yaml.safe_dump({"model_name": "csvq+swinT", "model": BASE}, open(mdir / "config.yaml", "w"))
+    x = synth_audio(1, 48000, seed=1)
+    save_wav(str(tmp_path / "clip.wav"), x, 16000)
+    x_rt, sr = load_wav(str(tmp_path / "clip.wav"))
+    assert sr == 16000 and torch.equal(x_rt, x)
+    for device in ("cuda", "cpu"):
+        out = tmp_path / f"out_{device}"
+        args = compress.parse_args(["--input", str(tmp_path / "clip.wav"), "--save_path", str(out),
+                                    "--model_path", str(mdir), "--num_streams", "6", "--device", device])
+        compress.main(args)
+        codes = torch.load(out / "encoded_9.0kbps_clip.pth", map_location="cpu")
+        wav, sr = load_wav(str(out / "decoded_9.0kbps_clip.wav"))
+        o = make_oracle(BASE, 0)[0]
+        ref_codes, fs = o.encode(x, 6)
+        assert torch.equal(codes, ref_codes)
+        assert maxabs(wav, o.decode(ref_codes, fs)) <= AUDIO_TOL
