@@ -229,17 +229,22 @@ struct Packer {
         TcWeight& w = gw.tc;
         w.N = gw.N;
         w.K = gw.K;
-        w.ntn = (gw.N + tc::MAX_BN - 1) / tc::MAX_BN;
-        w.BN = round_up((gw.N + w.ntn - 1) / w.ntn, 16);
-        w.nkb = (gw.K + tc::KB - 1) / tc::KB;
+        const tc::Tiling tl = tc::choose_tiling(gw.N, gw.K);
+        w.ntn = tl.ntn;
+        w.nsub = tl.nsub;
+        w.BN = tl.BN;
+        w.nkb = tl.nkb;
+        w.resident = tl.resident;
         const size_t img = (size_t)w.BN * 32;                 // floats per image
-        std::vector<float> out((size_t)w.ntn * w.nkb * 2 * img, 0.f);
-        for (int nt = 0; nt < w.ntn; ++nt)
+        const int nst = w.ntn * w.nsub;                       // sub-tiles; stage order (tile, kb, sub)
+        std::vector<float> out((size_t)nst * w.nkb * 2 * img, 0.f);
+        for (int st = 0; st < nst; ++st)
             for (int kb = 0; kb < w.nkb; ++kb) {
-                float* hi = out.data() + ((size_t)nt * w.nkb + kb) * 2 * img;
+                const int nt = st / w.nsub, sub = st % w.nsub;
+                float* hi = out.data() + (((size_t)nt * w.nkb + kb) * w.nsub + sub) * 2 * img;
                 float* lo = hi + img;
                 for (int r = 0; r < w.BN; ++r) {
-                    const int n = nt * w.BN + r;
+                    const int n = st * w.BN + r;
                     if (n >= gw.N) continue;
                     for (int kk = 0; kk < 32; ++kk) {
                         const int k = kb * 32 + kk;
@@ -260,7 +265,7 @@ struct Packer {
         gw.Kpad = round_up(K, kBK);
         gw.ldw = round_up(N, 4);
         gw.bias = nullptr;
-        gw.tc = TcWeight{nullptr, N, K, 0, 0, 0};
+        gw.tc = TcWeight{nullptr, N, K, 0, 0, 0, 0, 0};
         t.assign((size_t)gw.Kpad * gw.ldw, 0.f);
     }
 };
@@ -451,6 +456,7 @@ struct Work {
     float* qkv = nullptr;
     float* att = nullptr;
     float* hid = nullptr;
+    float2* stats = nullptr;                   // LayerNorm (mean, rstd) per logical GEMM row
     float* ze = nullptr;                       // projected VQ vectors [B*T][ldc(3d)]
     float* Y1 = nullptr;                       // de-embed pixel map [B][F][2W][ldc(C0)]
     long long* codes = nullptr;                // forward(): internal codes when the caller passes none
@@ -463,7 +469,7 @@ enum { WK_ENC = 1, WK_DEC = 2, WK_UNIT = 4 };
 static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp, Work& wk) {
     const int L = h->L;
     const int Wp = round_up(W, 4);
-    size_t max_tok = 0, max_qkv = 0, max_att = 0, max_hid = 0;
+    size_t max_tok = 0, max_qkv = 0, max_att = 0, max_hid = 0, max_rows = 0;
     for (int l = 0; l < L; ++l) {
         const int C = h->lev[l].C, H = h->lev[l].H, Hp = round_up(H, 4);
         const size_t M = (size_t)B * H * W, Mw = (size_t)B * Hp * Wp;
@@ -471,6 +477,7 @@ static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp
         max_qkv = std::max(max_qkv, Mw * ldc(3 * C));
         max_att = std::max(max_att, Mw * ldc(C));
         max_hid = std::max(max_hid, M * (size_t)(C * h->cfg.mlp_hidden_mult));
+        max_rows = std::max(max_rows, Mw);
     }
     wk.Sf = bp.take<float>((size_t)B * std::max(T, h->pt * W) * 2 * h->F);
     if (what & WK_ENC)
@@ -481,6 +488,7 @@ static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp
     wk.qkv = bp.take<float>(max_qkv);
     wk.att = bp.take<float>(max_att);
     wk.hid = bp.take<float>(max_hid);
+    wk.stats = bp.take<float2>(max_rows);
     int dmax = 0;
     for (int q = 0; q < L; ++q) dmax = std::max(dmax, h->cfg.codebook_dims[q]);
     wk.ze = bp.take<float>((size_t)B * (W / 2) * ldc(3 * dmax));
@@ -646,6 +654,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
         return fail(ESCB_ENOMEM, "workspace of %zu bytes is too small, %zu needed", ws_bytes, need);
     Bump bp(ws, ws_bytes);
     plan(h, B, W, T, what, bp, c.wk);
+    c.L.ln_stats = c.wk.stats;
     return ESCB_OK;
 }
 

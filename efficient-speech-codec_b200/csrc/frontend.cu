@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
+static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
 
 void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long Ls, int T, float* Sf) {
     L.begin(OP_STFT, 2.0 * B * T * f.win * 2 * f.F, 4.0 * (1.0 * B * Ls + 2.0 * B * T * f.F));

@@ -24,6 +24,7 @@ struct LnParams {
     const float* gamma;   // padded with zeros to a multiple of 4
     const float* beta;
     float eps;
+    float2* stats;        // [M] (mean, rstd) scratch of the tcgen05 engine's ln_stats_kernel (unused by the SIMT engine)
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -33,6 +34,11 @@ __device__ __forceinline__ float4 mask4(float4 v, int k, int K) {
     if (k + 2 >= K) v.z = 0.f;
     if (k + 3 >= K) v.w = 0.f;
     return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// L2 prefetch of elements [0, n) of a row, 128 bytes per probe, probes interleaved over `half` in {0, 1}
+__device__ __forceinline__ void prefetch_row(const float* p, int n, int half) {
+    for (int k = half * 32; k < n; k += 64) prefetch_l2(p + k);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -192,7 +198,8 @@ gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const 
 // lo = tf32(w - hi).  img == nullptr: this weight has no tensor-core image.
 struct TcWeight {
     const float* img;
-    int N, K, BN, ntn, nkb;
+    int N, K, BN, nsub, ntn, nkb;     // ntn output tiles of nsub sub-tiles of BN columns (tc::choose_tiling)
+    int resident;       // the whole n-tile (nkb K blocks) stays in shared memory for the life of a CTA
 };
 
 struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be null

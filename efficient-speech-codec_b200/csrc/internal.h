@@ -64,6 +64,7 @@ struct Launcher {                                    // stream + launch accounti
     cudaError_t err = cudaSuccess;
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
+    float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
     bool open = false;
     // flops / bytes: ALGORITHMIC work of the launch that follows (true dims, no padding, no 3x anything)
     void begin(int op, double flops, double bytes) {

@@ -22,6 +22,7 @@ struct ARows {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(r.p, K, half); }
 };
 
 // Window partition of a [B,H,W,C] token map zero-padded to (Hp,Wp) and cyclically shifted by `shift`
@@ -30,17 +31,18 @@ struct ARows {
 // (the reference pads AFTER norm1, so they bypass LayerNorm).
 struct WindowGeom {
     int H, W, Hp, Wp, shift, nWw, nW;   // nW = (Hp/4)*(Wp/4)
-    __device__ __forceinline__ long long token(long long m) const {
-        const int t = (int)(m & 15);
-        const long long wi = m >> 4;
-        const int win = (int)(wi % nW);
-        const long long b = wi / nW;
-        const int wh = win / nWw, ww = win % nWw;
+    __device__ __forceinline__ long long token(long long m) const {   // m < 2^31 (checked by the launchers)
+        const unsigned mm = (unsigned)m;
+        const int t = (int)(mm & 15u);
+        const unsigned wi = mm >> 4;
+        const unsigned b = wi / (unsigned)nW;
+        const unsigned win = wi - b * (unsigned)nW;
+        const int wh = (int)(win / (unsigned)nWw), ww = (int)(win - (unsigned)wh * (unsigned)nWw);
         int h = wh * 4 + (t >> 2) + shift, w = ww * 4 + (t & 3) + shift;
         if (h >= Hp) h -= Hp;
         if (w >= Wp) w -= Wp;
         if (h >= H || w >= W) return -1;
-        return (b * H + h) * (long long)W + w;
+        return ((long long)b * H + h) * (long long)W + w;
     }
 };
 
@@ -59,6 +61,7 @@ struct AWindow {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(r.p, K, half); }
 };
 
 // PatchMerge gather (scale.py:7-14,104-112): row m = (b, h2, w) is [ x[b,2*h2,w,:] ; x[b,2*h2+1,w,:] ], K = 2C.
@@ -69,12 +72,10 @@ struct AMerge {
     __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
         r.p0 = r.p1 = nullptr;
         if (m < M) {
-            const int H2 = H >> 1;
-            const int w = (int)(m % W);
-            const long long bh = m / W;
-            const int h2 = (int)(bh % H2);
-            const long long b = bh / H2;
-            r.p0 = X + ((b * H + 2 * h2) * (long long)W + w) * ld;
+            const unsigned H2 = (unsigned)H >> 1, mm = (unsigned)m;
+            const unsigned bh = mm / (unsigned)W, w = mm - bh * (unsigned)W;
+            const unsigned b = bh / H2, h2 = bh - b * H2;
+            r.p0 = X + (((long long)b * H + 2 * h2) * (long long)W + w) * ld;
             r.p1 = r.p0 + (long long)W * ld;
         }
     }
@@ -89,6 +90,7 @@ struct AMerge {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(half ? r.p1 : r.p0, C, 0); }
 };
 
 // Product-VQ frame of the residual enc - dec (csrvq.py:15-17; quantization.py:400-409).  The reference's frame
@@ -102,10 +104,9 @@ struct AFrame {
     __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
         r.base = -1;
         if (m < M) {
-            const int T = W >> 1;
-            const int t = (int)(m % T);
-            const long long b = m / T;
-            r.base = (b * Hq * (long long)W + 2 * t) * C;
+            const unsigned T = (unsigned)W >> 1, mm = (unsigned)m;
+            const unsigned b = mm / T, t = mm - b * T;
+            r.base = ((long long)b * Hq * (long long)W + 2 * t) * C;
         }
     }
     __device__ __forceinline__ bool valid(const Row& r) const { return r.base >= 0; }
@@ -126,6 +127,7 @@ struct AFrame {
         }
         return e;
     }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
 // Rows of de-quantised codebook vectors [z_q0 ; z_q1 ; z_q2] gathered from the RAW tables by code
@@ -158,6 +160,7 @@ struct ACodes {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
 // im2col of the 5x5 / pad 2 convolution over channels-last tokens [B,H,W,ld] (scale.py:66-68,77).
@@ -169,8 +172,9 @@ struct AIm2col {
     __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
         r.p = nullptr; r.h = r.w = 0;
         if (m < M) {
-            r.w = (int)(m % W);
-            r.h = (int)((m / W) % H);
+            const unsigned mm = (unsigned)m, q = mm / (unsigned)W;
+            r.w = (int)(mm - q * (unsigned)W);
+            r.h = (int)(q % (unsigned)H);
             r.p = X + m * (long long)ld;
         }
     }
@@ -187,6 +191,7 @@ struct AIm2col {
         if (hh < 0 || hh >= H || ww < 0 || ww >= W) return zero4();
         return mask4(ldg4(r.p + ((long long)dh * W + dw) * ld + c), c, C);
     }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
 // STFT framing with centre/reflect padding (base.py:22-24,36 -> torch.stft): row m = (b, t), element k is
@@ -219,6 +224,7 @@ struct AStftFrames {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
 // Inverse STFT as one GEMM (base.py:25-27,46-47 -> torch.istft): output chunk j (hop samples) sums the
@@ -246,6 +252,7 @@ struct AIstft {
         const int t = r.j - dt;
         return (t >= 0 && t < T) ? ldg4(r.p + (long long)t * F2 + cf) : zero4();
     }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
 // =============================================================================================== epilogues
@@ -257,26 +264,32 @@ struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
     const float* bias;
     const float* R;
     int ldy, ldr;
-    struct Row { float* y; const float* r; };
+    struct Row { long long y, r; };   // element offsets (not pointers: keeps the accesses in the global window)
     __device__ __forceinline__ bool row(long long m, Row& c) const {
-        c.y = Y + m * (long long)ldy;
-        c.r = RES ? R + m * (long long)ldr : nullptr;
+        c.y = m * (long long)ldy;
+        c.r = RES ? m * (long long)ldr : 0;
         return true;
     }
     __device__ __forceinline__ void store(const Row& c, int n, float v) const {
         if (bias) v += __ldg(bias + n);
         if (GELU) v = gelu_erf(v);
-        if (RES) v = c.r[n] + v;
-        c.y[n] = v;
+        if (RES) v = R[c.r + n] + v;
+        Y[c.y + n] = v;
     }
     __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {   // n % 4 == 0, ldy % 4 == 0
-        if (bias) { const float4 b = ldg4(bias + n); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        const float4 b = bias4(n);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        store4_nb(c, n, v);
+    }
+    // tcgen05 epilogue: the bias of a column chunk is fetched once (bias4) and added by the caller
+    __device__ __forceinline__ float4 bias4(int n) const { return bias ? ldg4(bias + n) : zero4(); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
         if (GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
         if (RES) {
-            const float4 r = *reinterpret_cast<const float4*>(c.r + n);
+            const float4 r = *reinterpret_cast<const float4*>(R + c.r + n);
             v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
         }
-        *reinterpret_cast<float4*>(c.y + n) = v;
+        *reinterpret_cast<float4*>(Y + c.y + n) = v;
     }
 };
 
@@ -302,31 +315,38 @@ struct EpiWindow {
         v.x = r.x + (v.x + b.x); v.y = r.y + (v.y + b.y); v.z = r.z + (v.z + b.z); v.w = r.w + (v.w + b.w);
         *reinterpret_cast<float4*>(Y + c.off + n) = v;
     }
+    __device__ __forceinline__ float4 bias4(int n) const { return ldg4(bias + n); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
+        const float4 r = *reinterpret_cast<const float4*>(R + c.off + n);
+        v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+        *reinterpret_cast<float4*>(Y + c.off + n) = v;
+    }
 };
 
 // PatchSplit pixel shuffle (scale.py:16-23,142-144): row m = (b,h,w); n < Co goes to freq row 2h, the rest to 2h+1.
 struct EpiSplit {
     float* Y;
     int ldy, H, W, Co;
-    struct Row { float* y0; };
+    struct Row { long long y0; };
     __device__ __forceinline__ bool row(long long m, Row& c) const {
-        const int w = (int)(m % W);
-        const long long bh = m / W;     // b*H + h
-        c.y0 = Y + ((2 * bh) * (long long)W + w) * ldy;
+        const unsigned mm = (unsigned)m, bh = mm / (unsigned)W, w = mm - bh * (unsigned)W;     // bh = b*H + h
+        c.y0 = ((2LL * bh) * (long long)W + w) * ldy;
         return true;
     }
     __device__ __forceinline__ void store(const Row& c, int n, float v) const {
-        if (n < Co) c.y0[n] = v;
-        else c.y0[(long long)W * ldy + (n - Co)] = v;
+        if (n < Co) Y[c.y0 + n] = v;
+        else Y[c.y0 + (long long)W * ldy + (n - Co)] = v;
     }
     __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
         if ((Co & 3) == 0) {
-            float* p = n < Co ? c.y0 + n : c.y0 + (long long)W * ldy + (n - Co);
+            float* p = n < Co ? Y + c.y0 + n : Y + c.y0 + (long long)W * ldy + (n - Co);
             *reinterpret_cast<float4*>(p) = v;
         } else {
             store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
         }
     }
+    __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
 };
 
 // product-VQ post_process + post_fuse (quantization.py:411-432; csrvq.py:19-21): column n' = (h, o, c) of frame
@@ -337,10 +357,9 @@ struct EpiFrame {
     int Hq, W, C;
     struct Row { long long base; };
     __device__ __forceinline__ bool row(long long m, Row& c) const {
-        const int T = W >> 1;
-        const int t = (int)(m % T);
-        const long long b = m / T;
-        c.base = (b * Hq * (long long)W + 2 * t) * C;
+        const unsigned T = (unsigned)W >> 1, mm = (unsigned)m;
+        const unsigned b = mm / T, t = mm - b * T;
+        c.base = ((long long)b * Hq * (long long)W + 2 * t) * C;
         return true;
     }
     __device__ __forceinline__ void store(const Row& c, int n, float v) const {
@@ -354,6 +373,8 @@ struct EpiFrame {
         if (D) { const float4 d = *reinterpret_cast<const float4*>(D + o); v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w; }
         *reinterpret_cast<float4*>(Y + o) = v;
     }
+    __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
 };
 
 // conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78):
@@ -362,20 +383,24 @@ struct EpiDeembed {
     float* Y;
     const float* bias;
     int ldy, H, W, C, pf, pt;
-    struct Row { float* y; };
+    struct Row { long long y; };
     __device__ __forceinline__ bool row(long long m, Row& c) const {
-        const int w = (int)(m % W);
-        const long long bh = m / W;
-        c.y = Y + ((bh * pf) * (long long)(W * pt) + (long long)w * pt) * ldy;
+        const unsigned mm = (unsigned)m, bh = mm / (unsigned)W, w = mm - bh * (unsigned)W;
+        c.y = (((long long)bh * pf) * (long long)(W * pt) + (long long)w * pt) * ldy;
         return true;
     }
-    __device__ __forceinline__ void store(const Row& c, int n, float v) const {
+    __device__ __forceinline__ void put(const Row& c, int n, float v) const {
         const int s = n / C, ch = n - s * C;
         const int s1 = s / pt, s2 = s - s1 * pt;
-        c.y[((long long)s1 * (W * pt) + s2) * ldy + ch] = v + __ldg(bias + n);
+        Y[c.y + ((long long)s1 * (W * pt) + s2) * ldy + ch] = v;
     }
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const { put(c, n, v + __ldg(bias + n)); }
     __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
         store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
+    }
+    __device__ __forceinline__ float4 bias4(int n) const { return ldg4(bias + n); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
+        put(c, n, v.x); put(c, n + 1, v.y); put(c, n + 2, v.z); put(c, n + 3, v.w);
     }
 };
 
@@ -404,6 +429,8 @@ struct EpiIstft {
     __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
         store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
     }
+    __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
 };
 
 }  // namespace escb

@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
+static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
 
 void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz) {
     AFrame al{enc, dec, q.in_freq, W, q.in_dim};

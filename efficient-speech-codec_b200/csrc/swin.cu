@@ -5,15 +5,15 @@
 
 namespace escb {
 
-static inline LnParams lnp(const LnW& w) { return LnParams{w.g, w.b, kLnEps}; }
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f}; }
+static inline LnParams lnp(const Launcher& L, const LnW& w) { return LnParams{w.g, w.b, kLnEps, L.ln_stats}; }
+static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
 
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq) {
     L.begin(OP_QKV, 2.0 * M * w.qkv.N * w.qkv.K, 4.0 * (1.0 * M * w.qkv.K + 1.0 * M * w.qkv.N));
     AWindow al{x, ld, g};
     EpiRows<false, false> ep{qkv, w.qkv.bias, nullptr, ldq, 0};
-    if (L.tc) L.note(tc::launch<true, AWindow, EpiRows<false, false>>(L.st, al, lnp(w.n1), w.qkv, M, ep));
-    else L.note(GemmLauncher<true, AWindow, EpiRows<false, false>, 7, 9>::launch(L.st, al, lnp(w.n1), w.qkv, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, AWindow, EpiRows<false, false>>(L.st, al, lnp(L, w.n1), w.qkv, M, ep));
+    else L.note(GemmLauncher<true, AWindow, EpiRows<false, false>, 7, 9>::launch(L.st, al, lnp(L, w.n1), w.qkv, M, ep));
 }
 
 void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
@@ -29,8 +29,8 @@ void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, 
     L.begin(OP_MLP1, 2.0 * M * w.fc1.N * w.fc1.K, 4.0 * M * (w.fc1.K + w.fc1.N));
     ARows al{x, ld};
     EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
-    if (L.tc) L.note(tc::launch<true, ARows, EpiRows<true, false>>(L.st, al, lnp(w.n2), w.fc1, M, ep));
-    else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(w.n2), w.fc1, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
+    else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
 }
 
 void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long M, float* x, int ld) {
@@ -46,8 +46,8 @@ void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     EpiRows<false, false> ep{y, nullptr, nullptr, ldy, 0};
     const long long M = (long long)B * (H / 2) * W;
     L.begin(OP_MERGE, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
-    if (L.tc) L.note(tc::launch<true, AMerge, EpiRows<false, false>>(L.st, al, lnp(w.sn), w.sub, M, ep));
-    else L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(w.sn), w.sub, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, AMerge, EpiRows<false, false>>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+    else L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 
 void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {
@@ -55,8 +55,8 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     EpiSplit ep{y, ldy, H, W, w.out_dim};
     const long long M = (long long)B * H * W;
     L.begin(OP_SPLIT, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
-    if (L.tc) L.note(tc::launch<true, ARows, EpiSplit>(L.st, al, lnp(w.sn), w.sub, M, ep));
-    else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(w.sn), w.sub, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+    else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 
 // ------------------------------------------------------------------------------------------------ attention

@@ -6,18 +6,23 @@
 // 3..742 of 3600 codes per stream (hard part 1).  Every operand x is split into
 // hi = tf32(x), lo = tf32(x - hi); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi in the fp32 TMEM accumulator
 // (the dropped lo*lo term is 2^-22 relative).  Weights are split once at escb_finalize(); activations are split
-// by the A-producer threads after the fused gather / LayerNorm.
+// by the A-producer warps after the fused gather / LayerNorm.
 //
-// Structure of one CTA (one 128 x BN output tile, 256 threads, 2 CTAs per SM so one CTA's epilogue overlaps the
-// other's main loop):
-//   * B operand: pre-swizzled smem images of the weights in HBM, fetched per 32-wide K block with ONE
-//     cp.async.bulk (TMA bulk engine, SASS UBLKCP) into a 2-stage ring, completion on an mbarrier;
-//   * A operand: each thread gathers 4 float4 of the logical rows (window partition + cyclic shift, frequency-row
-//     pairing, im2col ... same loaders as the SIMT engine), applies LayerNorm, splits hi/lo and writes the
-//     128-byte-swizzled K-major layout tcgen05 expects; the loads of block k+1 are in flight while block k runs;
-//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 3 per k-step and tcgen05.commit;
-//   * epilogue: 8 warps read the accumulator with tcgen05.ld 32x32b (one row per thread, 16 columns a time)
-//     and apply bias / GELU / residual / scatter through the same epilogue functors as the SIMT engine.
+// One persistent CTA per SM (576 threads), warp-specialised, looping over 128 x BN output tiles:
+//   warps 0-7   epilogue : tcgen05.ld the finished accumulator (one TMEM lane quadrant x one column half per warp),
+//                          transpose 32x16 chunks through a swizzled smem staging tile so that global stores and
+//                          residual loads are 64-byte row segments, apply bias / GELU / residual / scatter functor;
+//   warps 8-15  producer : gather the logical A rows (window partition + cyclic shift, frequency-row pairing,
+//                          im2col ... loaders.cuh), LayerNorm, cvt.rna.tf32 split, write the hi / lo images of a
+//                          32-wide K block in the 128-byte-swizzled K-major layout into a 3-slot ring; the next
+//                          tile is prefetched into L2 and its LayerNorm statistics are computed while the tensor
+//                          core drains the ring;
+//   warp 16     MMA      : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 3 per
+//                          k-step; tcgen05.commit releases the A slot / weight slot and publishes the accumulator;
+//   warp 17     weights  : pre-swizzled [hi | lo] weight images, ONE cp.async.bulk (SASS UBLKCP) per K block.
+//                          Layers whose whole n-tile fits (nkb * BN * 256 B <= ~108 KB) keep it RESIDENT in smem
+//                          for the life of the CTA; the others stream it through a 2..8 slot ring.
+// Two 256-column TMEM accumulators alternate between tiles, so the epilogue of tile t overlaps the MMAs of t+1.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +34,21 @@ namespace tc {
 
 constexpr int BM = 128;               // UMMA M
 constexpr int KB = 32;                // tf32 per 128-byte swizzle row = one K block
-constexpr int THREADS = 256;
-constexpr int MAX_BN = 144;
-constexpr int A_BYTES = 2 * BM * 128; // hi + lo images of one A block
+constexpr int EPI_WARPS = 8;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;
+constexpr int NA = 3;                 // A ring slots
+constexpr int MAX_NB = 8;             // weight ring slots (upper bound)
+constexpr int MAX_BN = 208;
+constexpr int A_SLOT = 2 * BM * 128;  // hi + lo images of one A block
+constexpr int ACC_STRIDE = 256;       // TMEM columns between the two accumulators
+constexpr int STG_BYTES = EPI_WARPS * 32 * 16 * 4;
+constexpr int CTX_BYTES = EPI_WARPS * 32 * 16;
+constexpr int NBARS = 2 * NA + 2 * MAX_NB + 4;
+constexpr int TAIL_BYTES = STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4 + NBARS * 8 + 16;
+constexpr int SMEM_MAX = 232448;      // 227 KB opt-in limit per CTA
+constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -41,16 +58,26 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Parity wait.  A healthy wait lasts microseconds; after ~2 s of spinning the kernel traps (a launch failure the
+// caller sees as ESCB_ECUDA) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
-    do {
+    long long t0 = 0;
+    for (;;) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
+    }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -116,200 +143,361 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 }
 
 template <bool LN, class AL, class EP>
-__global__ void __launch_bounds__(THREADS, 2)
-tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int tmem_cols) {
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
+               const int NB, const int resident) {
+    static_assert(sizeof(typename EP::Row) <= 16, "epilogue row context must fit 16 bytes");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ typename AL::Row rows[BM];
-    __shared__ __align__(8) uint64_t bars[3];          // [0],[1]: B stage landed; [2]: MMAs of a K block retired
-    __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = blockIdx.x % w.ntn;
-    const long long m0 = (long long)(blockIdx.x / w.ntn) * BM;
-    const int K = w.K, BN = w.BN, nkb = w.nkb;
+    const int K = w.K, BN = w.BN, nkb = w.nkb, ntn = w.ntn, nsub = w.nsub;
+    const int NT = BN * nsub;                             // columns of one output tile
 
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t sA = smem_u32(smem);                   // A hi image, then A lo image (16 KB each)
-    const uint32_t sB = sA + A_BYTES;                     // 2 stages x (hi image, lo image), BN x 128 B each
+    // 1024-byte alignment for the 128-byte swizzle atoms, as an offset so the pointers stay in the shared window
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sA = smem_u32(smem);                    // NA slots x (hi image, lo image), 16 KB each
     const uint32_t b_img = (uint32_t)BN * 128u, b_stage = 2u * b_img;
-    const uint32_t bar0 = smem_u32(&bars[0]);
+    const uint32_t sB = sA + NA * A_SLOT;                  // NB slots x (hi image, lo image), BN x 128 B each
+    uint8_t* tail = smem + NA * A_SLOT + (size_t)NB * b_stage;
+    float* stg_all = reinterpret_cast<float*>(tail);
+    typename EP::Row* ectx_all = reinterpret_cast<typename EP::Row*>(tail + STG_BYTES);
+    int* eok_all = reinterpret_cast<int*>(tail + STG_BYTES + CTX_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail + STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+    const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * NA, b_full = a_empty + 8 * NA,
+                   b_empty = b_full + 8 * MAX_NB, acc_full = b_empty + 8 * MAX_NB, acc_empty = acc_full + 16;
 
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tmem_cols);
-    if (tid == 32) {
-        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
+    if (warp == EPI_WARPS + PROD_WARPS) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (tid == THREADS - 32) {
+        for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, PROD_THREADS); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < MAX_NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, EPI_WARPS * 32); }
         fence_barrier_init();
     }
-    for (int r = tid; r < BM; r += THREADS) al.init(m0 + r, M, rows[r]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = *tmem_slot;
 
-    const uint8_t* wimg = (const uint8_t*)w.img + (size_t)nt * nkb * b_stage;
-    if (tid == 0) {
-        for (int s = 0; s < 2 && s < nkb; ++s) {
-            mbar_expect_tx(bar0 + 8 * s, b_stage);
-            bulk_g2s(sB + s * b_stage, wimg + (size_t)s * b_stage, b_stage, bar0 + 8 * s);
-        }
-    }
-
-    // A producer mapping: 16-byte chunk c of the 128-byte row, rows r0 + 32 i (8 consecutive lanes share a row)
-    const int c = tid & 7, r0 = tid >> 3;
-    typename AL::Row myrow[4];
-    bool vld[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { myrow[i] = rows[r0 + 32 * i]; vld[i] = al.valid(myrow[i]); }
-
-    float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {0.f, 0.f, 0.f, 0.f};
-    if (LN) {   // per-row mean / rstd, two passes; every load of a pass is independent (second pass hits L1/L2)
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int k = kb * KB + c * 4;
-            if (k < K) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (vld[i]) { const float4 v = al.load4(myrow[i], k, K); s[i] += (v.x + v.y) + (v.z + v.w); }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 4);
-            mean[i] = s[i] / (float)K;
-            s[i] = 0.f;
-        }
-#pragma unroll 4
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int k = kb * KB + c * 4;
-            if (k < K) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (vld[i]) {
-                        const float4 v = al.load4(myrow[i], k, K);
-                        float d = v.x - mean[i]; s[i] = fmaf(d, d, s[i]);
-                        if (k + 1 < K) { d = v.y - mean[i]; s[i] = fmaf(d, d, s[i]); }
-                        if (k + 2 < K) { d = v.z - mean[i]; s[i] = fmaf(d, d, s[i]); }
-                        if (k + 3 < K) { d = v.w - mean[i]; s[i] = fmaf(d, d, s[i]); }
-                    }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 1);
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 2);
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], 4);
-            rstd[i] = 1.0f / sqrtf(s[i] / (float)K + ln.eps);
-        }
-    }
-
-    float4 a[4];
-    auto load_a = [&](int kb) {
-        const int k = kb * KB + c * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (vld[i] && k < K) ? al.load4(myrow[i], k, K) : zero4();
-    };
-    load_a(0);
-
-    const uint32_t idesc = make_idesc(BN);
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int k = kb * KB + c * 4;
-        float4 g = zero4(), be = zero4();
-        if (LN && k < K) { g = ldg4(ln.gamma + k); be = ldg4(ln.beta + k); }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = r0 + 32 * i;
-            float4 v = a[i];
-            if (LN && k < K && vld[i]) {
-                v.x = (v.x - mean[i]) * rstd[i] * g.x + be.x;
-                v.y = (v.y - mean[i]) * rstd[i] * g.y + be.y;
-                v.z = (v.z - mean[i]) * rstd[i] * g.z + be.z;
-                v.w = (v.w - mean[i]) * rstd[i] * g.w + be.w;
-                v = mask4(v, k, K);
-            }
-            float4 hi, lo;
-            split4(v, hi, lo);
-            const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4);
-            *reinterpret_cast<float4*>(smem + off) = hi;
-            *reinterpret_cast<float4*>(smem + BM * 128 + off) = lo;
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            const int s = kb & 1;
-            mbar_wait(bar0 + 8 * s, (uint32_t)((kb >> 1) & 1));
-            tc_fence_after();
-            int rem = K - kb * KB;
-            if (rem > KB) rem = KB;
-            const int ksteps = (rem + 7) >> 3;
-            const uint64_t a_hi = make_desc(sA), a_lo = make_desc(sA + BM * 128);
-            const uint64_t b_hi = make_desc(sB + s * b_stage), b_lo = make_desc(sB + s * b_stage + b_img);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes >> 4 inside the swizzle row
-                umma_tf32(tmem, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);
-                umma_tf32(tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                umma_tf32(tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-            }
-            umma_commit(bar0 + 16);
-        }
-        if (kb + 1 < nkb) load_a(kb + 1);
-        mbar_wait(bar0 + 16, (uint32_t)(kb & 1));
-        if (tid == 0 && kb + 2 < nkb) {
-            const int s = kb & 1;
-            mbar_expect_tx(bar0 + 8 * s, b_stage);
-            bulk_g2s(sB + s * b_stage, wimg + (size_t)(kb + 2) * b_stage, b_stage, bar0 + 8 * s);
-        }
-    }
-    tc_fence_after();
-
-    // epilogue: warp -> TMEM lane quadrant (warp & 3), column chunks of 16 interleaved over the two warp halves
-    {
+    if (warp < EPI_WARPS) {
+        // ======================================================================================== epilogue
         const int q = warp & 3, half = warp >> 2;
-        const int r = q * 32 + lane;
-        const long long m = m0 + r;
-        typename EP::Row er;
-        bool ok = m < M;
-        if (ok) ok = ep.row(m, er);
-        const int n0 = nt * BN, N = w.N;
-        for (int ch = half; ch < BN / 16; ch += 2) {
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
-            if (ok) {
+        float* stg = stg_all + warp * (32 * 16);
+        typename EP::Row* ectx = ectx_all + warp * 32;
+        int* eok = eok_all + warp * 32;
+        const int nch = NT >> 4, N = w.N;
+        const int rr = lane >> 2, c4 = lane & 3;           // transposed side: rows rr + 8 i, 16-byte chunk c4
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            const long long m = (long long)(tile / ntn) * BM + q * 32 + lane;
+            const int n0 = (tile % ntn) * NT;
+            typename EP::Row er;
+            int ok = m < M;
+            if (ok) ok = ep.row(m, er) ? 1 : 0;
+            __syncwarp();
+            ectx[lane] = er;
+            eok[lane] = ok;
+            mbar_wait(acc_full + 8 * buf, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + buf * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            for (int ch = half; ch < nch; ch += 2) {
+                float v[16];
+                tmem_ld16(tbase + (uint32_t)(ch * 16), v);
+                __syncwarp();                              // previous chunk's reads of the staging tile are done
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const int n = n0 + ch * 16 + j;
-                    if (n + 3 < N) {
-                        ep.store4(er, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int n = n0 + ch * 16 + c4 * 4;
+                const bool full4 = n + 3 < N;
+                const float4 b4 = full4 ? ep.bias4(n) : zero4();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rr + 8 * i;
+                    if (!eok[r] || n >= N) continue;
+                    float4 o = *reinterpret_cast<const float4*>(stg + r * 16 + ((c4 ^ ((r >> 1) & 3)) << 2));
+                    const typename EP::Row cr = ectx[r];
+                    if (full4) {
+                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                        ep.store4_nb(cr, n, o);
                     } else {
+                        ep.store(cr, n, o.x);
+                        if (n + 1 < N) ep.store(cr, n + 1, o.y);
+                        if (n + 2 < N) ep.store(cr, n + 2, o.z);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8 * buf);
+        }
+    } else if (warp < EPI_WARPS + PROD_WARPS) {
+        // ======================================================================================== A producer
+        // 16-byte chunk c of the 128-byte K-block row, rows r0 + 32 i (8 consecutive lanes share a row).  The
+        // (tile, K block) jobs of this CTA form one flat stream; the loads of job j+2 are issued before job j is
+        // converted, so two K blocks of global loads (plus the L2 prefetch of the following tile) are always in
+        // flight and tile boundaries cost nothing.  LayerNorm statistics come from ln_stats_kernel.
+        const int pt = tid - EPI_WARPS * 32;
+        const int c = pt & 7, r0 = pt >> 3;
+        typename AL::Row myrow[4];
+        unsigned cur_vm = 0;
+        long long cur_m0 = 0;
+        int ld_tile = blockIdx.x, ld_kb = 0;
+
+        auto issue = [&](float4 (&a)[4], float2 (&st)[4], unsigned& vm, int& kk) -> bool {
+            if (ld_tile >= ntiles) return false;
+            if (ld_kb == 0) {
+                cur_m0 = (long long)(ld_tile / ntn) * BM;
+                cur_vm = 0;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (n + u < N) ep.store(er, n + u, v[j + u]);
+                for (int i = 0; i < 4; ++i) {
+                    al.init(cur_m0 + r0 + 32 * i, M, myrow[i]);
+                    if (al.valid(myrow[i])) cur_vm |= 1u << i;
+                }
+                const int next = ld_tile + gridDim.x;
+                if (next < ntiles) {                       // pull the following tile's rows into L2 (two threads per row)
+                    typename AL::Row pr;
+                    al.init((long long)(next / ntn) * BM + (pt >> 1), M, pr);
+                    if (al.valid(pr)) al.prefetch(pr, K, pt & 1);
+                }
+            }
+            const int k = ld_kb * KB + c * 4;
+            kk = k;
+            vm = cur_vm;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool on = ((cur_vm >> i) & 1u) && k < K;
+                a[i] = on ? al.load4(myrow[i], k, K) : zero4();
+                if (LN) st[i] = on ? __ldg(ln.stats + cur_m0 + r0 + 32 * i) : make_float2(0.f, 0.f);
+            }
+            if (++ld_kb == nkb) { ld_kb = 0; ld_tile += gridDim.x; }
+            return true;
+        };
+
+        uint32_t slot = 0, phase = 0;                     // ring position of the next K block
+        auto convert = [&](const float4 (&a)[4], const float2 (&st)[4], const unsigned vm, const int k) {
+            float4 g = zero4(), be = zero4();
+            if (LN && k < K) { g = ldg4(ln.gamma + k); be = ldg4(ln.beta + k); }
+            mbar_wait(a_empty + 8 * slot, phase ^ 1);
+            uint8_t* dst = smem + slot * A_SLOT;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 32 * i;
+                float4 v = a[i];
+                if (LN && k < K && ((vm >> i) & 1u)) {
+                    const float mean = st[i].x, rstd = st[i].y;
+                    v.x = (v.x - mean) * rstd * g.x + be.x;
+                    v.y = (v.y - mean) * rstd * g.y + be.y;
+                    v.z = (v.z - mean) * rstd * g.z + be.z;
+                    v.w = (v.w - mean) * rstd * g.w + be.w;
+                    v = mask4(v, k, K);
+                }
+                float4 hi, lo;
+                split4(v, hi, lo);
+                const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(c ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(dst + off) = hi;
+                *reinterpret_cast<float4*>(dst + BM * 128 + off) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(a_full + 8 * slot);
+            if (++slot == NA) { slot = 0; phase ^= 1; }
+        };
+
+        float4 a0[4], a1[4];
+        float2 s0[4], s1[4];
+        unsigned vm0 = 0, vm1 = 0;
+        int k0 = 0, k1 = 0;
+        bool h0 = issue(a0, s0, vm0, k0);
+        bool h1 = h0 && issue(a1, s1, vm1, k1);
+        while (h0) {
+            convert(a0, s0, vm0, k0);
+            h0 = issue(a0, s0, vm0, k0);
+            if (!h1) break;
+            convert(a1, s1, vm1, k1);
+            h1 = h0 && issue(a1, s1, vm1, k1);
+        }
+    } else if (warp == EPI_WARPS + PROD_WARPS) {
+        // ======================================================================================== MMA issuer
+        const uint32_t idesc = make_idesc(BN);
+        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1;
+            mbar_wait(acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + buf * ACC_STRIDE;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(a_full + 8 * aslot, aphase);
+                int rem = K - kb * KB;
+                if (rem > KB) rem = KB;
+                const int ksteps = (rem + 7) >> 3;
+                const uint64_t a_hi = make_desc(sA + aslot * A_SLOT), a_lo = make_desc(sA + aslot * A_SLOT + BM * 128);
+                for (int sub = 0; sub < nsub; ++sub) {
+                    const uint32_t bs = resident ? (uint32_t)(kb * nsub + sub) : bslot;
+                    mbar_wait(b_full + 8 * bs, resident ? 0u : bphase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t b_hi = make_desc(sB + bs * b_stage), b_lo = make_desc(sB + bs * b_stage + b_img);
+                        const uint32_t d_sub = d_tmem + (uint32_t)(sub * BN);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes >> 4 inside the swizzle row
+                            umma_tf32(d_sub, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);
+                            umma_tf32(d_sub, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d_sub, a_hi + adv, b_hi + adv, idesc, 1u);
+                        }
+                        if (!resident) umma_commit(b_empty + 8 * bs);
+                        if (sub + 1 == nsub) {
+                            umma_commit(a_empty + 8 * aslot);
+                            if (kb + 1 == nkb) umma_commit(acc_full + 8 * buf);
+                        }
+                    }
+                    __syncwarp();
+                    if (!resident && ++bslot == (uint32_t)NB) { bslot = 0; bphase ^= 1; }
+                }
+                if (++aslot == NA) { aslot = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ======================================================================================== weight loader
+        if (lane == 0) {
+            const uint8_t* wimg = (const uint8_t*)w.img;
+            if (resident) {
+                if ((int)blockIdx.x < ntiles) {
+                    const int nt = blockIdx.x % ntn;          // grid is a multiple of ntn: fixed n-tile per CTA
+                    for (int j = 0; j < nkb * nsub; ++j) {         // stage j = kb * nsub + sub
+                        mbar_expect_tx(b_full + 8 * j, b_stage);
+                        bulk_g2s(sB + j * b_stage, wimg + ((size_t)nt * nkb * nsub + j) * b_stage, b_stage, b_full + 8 * j);
+                    }
+                }
+            } else {
+                uint32_t bslot = 0, bphase = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    const int nt = tile % ntn;
+                    for (int j = 0; j < nkb * nsub; ++j) {
+                        mbar_wait(b_empty + 8 * bslot, bphase ^ 1);
+                        mbar_expect_tx(b_full + 8 * bslot, b_stage);
+                        bulk_g2s(sB + bslot * b_stage, wimg + ((size_t)nt * nkb * nsub + j) * b_stage, b_stage, b_full + 8 * bslot);
+                        if (++bslot == (uint32_t)NB) { bslot = 0; bphase ^= 1; }
                     }
                 }
             }
         }
+        __syncwarp();
     }
+
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+    if (warp == EPI_WARPS + PROD_WARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512u);
+    }
+}
+
+// LayerNorm statistics of the logical A rows (mean, 1/sqrt(var + eps)): 8 lanes per row, the row held in
+// registers (K <= 384: 12 float4 per lane), two-pass (mean, then centred squares) like the reference's
+// layer_norm with a single read of the data and every load independent.
+constexpr int LN_MAX_K = 384;
+template <class AL>
+__global__ void __launch_bounds__(256)
+ln_stats_kernel(const AL al, const long long M, const int K, const float eps, float2* __restrict__ out) {
+    const int c = threadIdx.x & 7;
+    const long long m = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+    typename AL::Row r;
+    al.init(m, M, r);                                      // m >= M yields an invalid row
+    const bool ok = al.valid(r);
+    float4 v[LN_MAX_K / 32];
+#pragma unroll
+    for (int j = 0; j < LN_MAX_K / 32; ++j) {
+        const int k = (c + 8 * j) * 4;
+        v[j] = (ok && k < K) ? al.load4(r, k, K) : zero4();
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_K / 32; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mean = s / (float)K;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_K / 32; ++j) {
+        const int k = (c + 8 * j) * 4;
+        if (k < K) { const float d = v[j].x - mean; q = fmaf(d, d, q); }
+        if (k + 1 < K) { const float d = v[j].y - mean; q = fmaf(d, d, q); }
+        if (k + 2 < K) { const float d = v[j].z - mean; q = fmaf(d, d, q); }
+        if (k + 3 < K) { const float d = v[j].w - mean; q = fmaf(d, d, q); }
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    if (c == 0 && m < M) out[m] = ok ? make_float2(mean, 1.0f / sqrtf(q / (float)K + eps)) : make_float2(0.f, 0.f);
+}
+
+// Tiling of one weight, decided at pack time (api.cu put_tc): N is cut into ntn output tiles of nsub sub-tiles of
+// BN columns each (BN = the UMMA N and the granularity of the weight ring; nsub * BN <= 256 TMEM columns).  The
+// A operand is produced once per output tile, so wide tiles save producer work and L2 reads; the cost model is
+// L2 traffic per m-tile and K block (units of 256 bytes: 64 per A production, BN per streamed weight stage)
+// against tensor time (6 clocks per column ~ 0.94 units).
+struct Tiling { int BN, nsub, ntn, nkb, resident; };
+
+inline Tiling choose_tiling(int N, int K) {
+    Tiling best{0, 0, 0, 0, 0};
+    double best_cost = 1e30;
+    const int nkb = (K + KB - 1) / KB;
+    for (int ntn = 1; ntn <= 64; ++ntn)
+        for (int nsub = 1; nsub <= 4; ++nsub) {
+            const int bn = (((N + ntn * nsub - 1) / (ntn * nsub)) + 15) / 16 * 16;
+            if (bn > (nsub == 1 ? MAX_BN : 128) || bn * nsub > ACC_STRIDE) continue;
+            if (bn < 48 && ntn * nsub > 1) continue;
+            const long long stage = (long long)bn * 256;
+            const bool res = stage * nkb * nsub <= B_BUDGET && nkb * nsub <= MAX_NB;
+            const int nb = res ? nkb * nsub : (int)(B_BUDGET / stage);
+            if (!res && nb < 3 && nkb * nsub > 2) continue;
+            const double padn = (double)bn * nsub * ntn;
+            const double l2 = 64.0 * ntn + (res ? 0.0 : padn), mma = 0.94 * padn;
+            const double cost = (l2 > mma ? l2 : mma) + 0.1 * (l2 + padn) + (bn < 64 ? 0.3 * padn : 0.0);
+            if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0}; }
+        }
+    return best;
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 template <bool LN, class AL, class EP>
 inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
     const TcWeight& w = gw.tc;
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
-    const size_t smem = 1024 + A_BYTES + 2 * 2 * (size_t)w.BN * 128;
+    if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
     static bool configured = false;     // per instantiation
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)(1024 + A_BYTES + 4 * MAX_BN * 128));
+        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    if (LN) {
+        if (!ln.stats || w.K > LN_MAX_K) return cudaErrorInvalidValue;
+        ln_stats_kernel<AL><<<(unsigned)((M + 31) / 32), 256, 0, st>>>(al, M, w.K, ln.eps, ln.stats);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const long long stage = (long long)w.BN * 256;
+    const int NB = w.resident ? w.nkb * w.nsub : (int)(B_BUDGET / stage < MAX_NB ? B_BUDGET / stage : MAX_NB);
+    const size_t smem = 1024 + (size_t)NA * A_SLOT + (size_t)NB * stage + TAIL_BYTES;
     const long long ntm = (M + BM - 1) / BM;
-    const int cols = w.BN <= 32 ? 32 : (w.BN <= 64 ? 64 : (w.BN <= 128 ? 128 : 256));
-    tc_gemm_kernel<LN, AL, EP><<<(unsigned)(ntm * w.ntn), THREADS, smem, st>>>(al, ln, w, M, ep, cols);
+    const long long ntiles = ntm * w.ntn;
+    if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    long long grid = sm_count();
+    if (w.resident) grid = grid / w.ntn * w.ntn;       // a resident CTA serves one n-tile
+    if (grid > ntiles) grid = ntiles;
+    tc_gemm_kernel<LN, AL, EP><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident);
     return cudaGetLastError();
 }
 
