@@ -67,6 +67,7 @@ struct escb_handle {
     FrontW front;
     std::atomic<long long> launches{0};
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
+    bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     // grow-only scratch for the *_host entry points
     std::mutex host_mu;
@@ -340,6 +341,7 @@ static void pack_quant(Packer& P, int q) {
             }
     P.put(&qw.down.wt, down);
     P.put(&qw.up.wt, up);
+    P.put_tc(qw.up, up);
     // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
     std::vector<float> raw((size_t)3 * K * dd), cbt((size_t)3 * K * dd), cn((size_t)3 * K);
     for (int g = 0; g < 3; ++g) {
@@ -427,7 +429,11 @@ static void pack_front(Packer& P) {
         for (int c = 0; c < C0; ++c)
             for (int tap = 0; tap < 9; ++tap) de2[((size_t)tap * C0 + c) * 2 + o] = w2[((size_t)o * C0 + c) * 9 + tap];
     P.put(&f.de2_w, de2);
+    memset(&f.de2_k, 0, sizeof f.de2_k);
+    memcpy(f.de2_k.w, de2.data(), de2.size() * sizeof(float));
     P.put(&f.de2_b, P.w("decoder.patch_deembed.de_proj2.bias"));
+    f.de2_bias[0] = P.w("decoder.patch_deembed.de_proj2.bias")[0];
+    f.de2_bias[1] = P.w("decoder.patch_deembed.de_proj2.bias")[1];
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
@@ -647,6 +653,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.L.st = (cudaStream_t)stream;
     c.L.prof = h->prof;
     c.L.tc = h->use_tc;
+    c.L.pvq_tc = h->use_tc && h->pvq_tc;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -705,6 +712,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     escb_handle* h = new escb_handle();
     h->cfg = c;
     if (const char* e = getenv("ESCB_GEMM")) h->use_tc = strcmp(e, "simt") != 0;
+    if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
     h->F = c.in_freq; h->n_fft = n_fft; h->win = c.win_length; h->hop = c.hop_length;
@@ -719,7 +727,8 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
         }
     }
     build_manifest(h);
-    const cudaError_t e = swin_init();
+    cudaError_t e = swin_init();
+    if (e == cudaSuccess) e = frontend_init();
     if (e != cudaSuccess) {
         delete h;
         return fail(ESCB_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));

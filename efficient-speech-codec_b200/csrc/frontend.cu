@@ -7,6 +7,13 @@ namespace escb {
 
 static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
 
+static size_t conv3_smem_bytes(int ld) { return (size_t)(kC3F + 2) * ((kC3T + 2) * ld + 4) * sizeof(float); }
+
+cudaError_t frontend_init() {
+    return cudaFuncSetAttribute(conv3x3_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)conv3_smem_bytes(ldc(kEmbedMaxC)));
+}
+
 void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long Ls, int T, float* Sf) {
     L.begin(OP_STFT, 2.0 * B * T * f.win * 2 * f.F, 4.0 * (1.0 * B * Ls + 2.0 * B * T * f.F));
     AStftFrames al{audio, Ls, T, f.hop, f.win / 2};
@@ -31,10 +38,10 @@ void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, i
     else L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
     const int Fq = H * f.pf, T2 = W * f.pt;
     const long long total = (long long)B * Fq * T2;
-    const int threads = 128;
     L.begin(OP_DEEMBED2, 2.0 * total * 2 * 9 * f.C0, 4.0 * total * (f.C0 + 2.0));
-    conv3x3_out_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 9 * f.C0 * 2 * sizeof(float), L.st>>>(
-        Y1, ld, f.C0, Fq, T2, f.de2_w, f.de2_b, Xf, total);
+    dim3 grid((Fq + kC3F - 1) / kC3F, (T2 + kC3T - 1) / kC3T, B);
+    conv3x3_out_kernel<<<grid, 256, conv3_smem_bytes(ld), L.st>>>(Y1, ld, f.C0, Fq, T2, f.de2_k, f.de2_bias[0],
+                                                                 f.de2_bias[1], Xf);
     L.note(cudaGetLastError());
 }
 

@@ -38,6 +38,8 @@ struct QuantW {
     const float* cnorm;                              // [3][ncodes] squared norms of cbn rows
 };
 
+struct Conv3Weights { float w[9 * 64 * 2]; };        // [tap][c][2], c < kEmbedMaxC
+
 struct FrontW {
     int F, win, hop, nov, C0, pf, pt;
     GemmWeight dft;                                  // [win][2F] windowed DFT basis
@@ -46,6 +48,8 @@ struct FrontW {
     const float* embed_w; const float* embed_b; LnW embed_ln;
     GemmWeight de1;                                  // conv5x5 as implicit GEMM, K = 25*ldc(C0)
     const float* de2_w; const float* de2_b;          // [9][C0][2], [2]
+    float de2_bias[2];
+    Conv3Weights de2_k;                              // the same taps as a by-value kernel parameter (constant bank)
 };
 
 // Kernel classes for launch accounting / per-op timing (escb_profile_begin/end).
@@ -63,6 +67,7 @@ struct Launcher {                                    // stream + launch accounti
     long long launches = 0;
     cudaError_t err = cudaSuccess;
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
+    bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
     bool open = false;
@@ -98,6 +103,7 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
 void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
 void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
 cudaError_t swin_init();
+cudaError_t frontend_init();
 
 // ---- pvq.cu : product VQ of one stream
 void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "internal.h"
+
 namespace escb {
 
 // ------------------------------------------------------------------------------------------------ attention core
@@ -271,46 +273,56 @@ static __global__ void patch_embed_kernel(const float* __restrict__ Sf, const in
 // ------------------------------------------------------------------------------------------------ output conv
 // PatchDeEmbed.de_proj2 (scale.py:70-71,79): 3x3 / pad 1 convolution C0 -> 2 over the channels-last pixel map
 // Y1 [B, F, T2, ld]; writes the spectrum frame-major Xf[b, t, c2*F + f] (what the inverse STFT reads).
-// Packed weight: wp[tap][c][2].
-static __global__ void conv3x3_out_kernel(const float* __restrict__ Y1, const int ld, const int C0, const int F,
-                                   const int T2, const float* __restrict__ wp, const float* __restrict__ bias,
-                                   float* __restrict__ Xf, const long long total) {
-    extern __shared__ float swc[];   // 9*C0*2
-    for (int i = threadIdx.x; i < 9 * C0 * 2; i += blockDim.x) swc[i] = wp[i];
+// One block = 32 frequency bins x 8 frames: the (34 x 10) halo is staged in shared memory with coalesced float4
+// loads (row pitch padded by 4 floats so the 32 lanes of a warp, one bin each, read conflict-free), the taps
+// [tap][c][2] arrive as a by-value kernel parameter so every FMA takes its weight from the constant bank, and
+// lanes run along the bin axis so both output planes are written as 128-byte segments.
+constexpr int kC3F = 32, kC3T = 8;
+static __global__ void __launch_bounds__(256)
+conv3x3_out_kernel(const float* __restrict__ Y1, const int LD, const int C0, const int F, const int T2,
+                   const __grid_constant__ Conv3Weights wk, const float b0, const float b1, float* __restrict__ Xf) {
+    const int PITCH = (kC3T + 2) * LD + 4;
+    extern __shared__ __align__(16) float halo[];          // [kC3F + 2][PITCH]
+    const int f0 = blockIdx.x * kC3F, t0 = blockIdx.y * kC3T;
+    const long long b = blockIdx.z;
+    const int ROW4 = (kC3T + 2) * LD / 4;
+    for (int i = threadIdx.x; i < (kC3F + 2) * ROW4; i += 256) {
+        const int fr = i / ROW4, j = i - fr * ROW4;
+        const int tt = j / (LD / 4), c4 = j - tt * (LD / 4);
+        const int f = f0 + fr - 1, t = t0 + tt - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f >= 0 && f < F && t >= 0 && t < T2)
+            v = __ldg(reinterpret_cast<const float4*>(Y1 + ((b * F + f) * (long long)T2 + t) * LD) + c4);
+        *reinterpret_cast<float4*>(halo + fr * PITCH + tt * LD + c4 * 4) = v;
+    }
     __syncthreads();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int t = (int)(idx % T2);
-    const int f = (int)((idx / T2) % F);
-    const long long b = idx / ((long long)T2 * F);
+    const int fl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+    const int f = f0 + fl, t = t0 + tl;
     float a0 = 0.f, a1 = 0.f;
-    const int C4 = C0 & ~3;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int ff = f + kh - 1;
-        if (ff < 0 || ff >= F) continue;
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-            const int tt = t + kw - 1;
-            if (tt < 0 || tt >= T2) continue;
-            const float* p = Y1 + ((b * F + ff) * (long long)T2 + tt) * ld;
-            const float* wv = swc + (kh * 3 + kw) * C0 * 2;
-            for (int c = 0; c < C4; c += 4) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
+            const float* p = halo + (fl + kh) * PITCH + (tl + kw) * LD;
+            const float* wv = wk.w + (kh * 3 + kw) * C0 * 2;
+#pragma unroll 4
+            for (int c = 0; c + 3 < C0; c += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(p + c);
                 a0 = fmaf(v.x, wv[2 * c + 0], a0); a1 = fmaf(v.x, wv[2 * c + 1], a1);
                 a0 = fmaf(v.y, wv[2 * c + 2], a0); a1 = fmaf(v.y, wv[2 * c + 3], a1);
                 a0 = fmaf(v.z, wv[2 * c + 4], a0); a1 = fmaf(v.z, wv[2 * c + 5], a1);
                 a0 = fmaf(v.w, wv[2 * c + 6], a0); a1 = fmaf(v.w, wv[2 * c + 7], a1);
             }
-            for (int c = C4; c < C0; ++c) {
-                const float v = __ldg(p + c);
+            for (int c = C0 & ~3; c < C0; ++c) {
+                const float v = p[c];
                 a0 = fmaf(v, wv[2 * c], a0); a1 = fmaf(v, wv[2 * c + 1], a1);
             }
         }
+    if (f < F && t < T2) {
+        float* o = Xf + (b * T2 + t) * (long long)(2 * F);
+        o[f] = a0 + b0;
+        o[F + f] = a1 + b1;
     }
-    float* o = Xf + (b * T2 + t) * (long long)(2 * F);
-    o[f] = a0 + __ldg(bias);
-    o[F + f] = a1 + __ldg(bias + 1);
 }
 
 // ------------------------------------------------------------------------------------------------ layout helpers

@@ -61,22 +61,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Parity wait.  A healthy wait lasts microseconds; after ~2 s of spinning the kernel traps (a launch failure the
+// Parity wait.  try_wait suspends the warp in hardware (up to the hint, woken as soon as the phase completes), so
+// the loop rarely spins; a wait that is still pending after ~2 s of suspensions traps (a launch failure the
 // caller sees as ESCB_ECUDA) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    long long t0 = 0;
+    uint32_t done, spins = 0;
     for (;;) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
         if (done) break;
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000LL) __trap();
+        if (++spins > 400000u) __trap();
     }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -397,7 +395,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
 // registers (K <= 384: 12 float4 per lane), two-pass (mean, then centred squares) like the reference's
 // layer_norm with a single read of the data and every load independent.
 constexpr int LN_MAX_K = 384;
-template <class AL>
+template <int NCH, class AL>
 __global__ void __launch_bounds__(256)
 ln_stats_kernel(const AL al, const long long M, const int K, const float eps, float2* __restrict__ out) {
     const int c = threadIdx.x & 7;
@@ -405,22 +403,22 @@ ln_stats_kernel(const AL al, const long long M, const int K, const float eps, fl
     typename AL::Row r;
     al.init(m, M, r);                                      // m >= M yields an invalid row
     const bool ok = al.valid(r);
-    float4 v[LN_MAX_K / 32];
+    float4 v[NCH];
 #pragma unroll
-    for (int j = 0; j < LN_MAX_K / 32; ++j) {
+    for (int j = 0; j < NCH; ++j) {
         const int k = (c + 8 * j) * 4;
         v[j] = (ok && k < K) ? al.load4(r, k, K) : zero4();
     }
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_K / 32; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    for (int j = 0; j < NCH; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     const float mean = s / (float)K;
     float q = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_K / 32; ++j) {
+    for (int j = 0; j < NCH; ++j) {
         const int k = (c + 8 * j) * 4;
         if (k < K) { const float d = v[j].x - mean; q = fmaf(d, d, q); }
         if (k + 1 < K) { const float d = v[j].y - mean; q = fmaf(d, d, q); }
@@ -431,6 +429,17 @@ ln_stats_kernel(const AL al, const long long M, const int K, const float eps, fl
     q += __shfl_xor_sync(0xffffffffu, q, 2);
     q += __shfl_xor_sync(0xffffffffu, q, 4);
     if (c == 0 && m < M) out[m] = ok ? make_float2(mean, 1.0f / sqrtf(q / (float)K + eps)) : make_float2(0.f, 0.f);
+}
+
+template <class AL>
+inline cudaError_t launch_ln_stats(cudaStream_t st, const AL& al, long long M, int K, float eps, float2* out) {
+    const unsigned grid = (unsigned)((M + 31) / 32);
+    if (K <= 64) ln_stats_kernel<2, AL><<<grid, 256, 0, st>>>(al, M, K, eps, out);
+    else if (K <= 96) ln_stats_kernel<3, AL><<<grid, 256, 0, st>>>(al, M, K, eps, out);
+    else if (K <= 192) ln_stats_kernel<6, AL><<<grid, 256, 0, st>>>(al, M, K, eps, out);
+    else if (K <= LN_MAX_K) ln_stats_kernel<LN_MAX_K / 32, AL><<<grid, 256, 0, st>>>(al, M, K, eps, out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 // Tiling of one weight, decided at pack time (api.cu put_tc): N is cut into ntn output tiles of nsub sub-tiles of
@@ -483,9 +492,8 @@ inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, con
         configured = true;
     }
     if (LN) {
-        if (!ln.stats || w.K > LN_MAX_K) return cudaErrorInvalidValue;
-        ln_stats_kernel<AL><<<(unsigned)((M + 31) / 32), 256, 0, st>>>(al, M, w.K, ln.eps, ln.stats);
-        const cudaError_t e = cudaGetLastError();
+        if (!ln.stats) return cudaErrorInvalidValue;
+        const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
         if (e != cudaSuccess) return e;
     }
     const long long stage = (long long)w.BN * 256;
