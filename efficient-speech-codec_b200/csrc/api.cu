@@ -69,6 +69,7 @@ struct escb_handle {
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
+    unsigned long long* trace = nullptr;   // ESCB_TC_TRACE builds only
     // grow-only scratch for the *_host entry points
     std::mutex host_mu;
     void* host_scratch = nullptr;
@@ -205,7 +206,7 @@ struct Packer {
         put(&ln.b, b);
     }
     // Wt[k][n] = W[n][k] for a reference nn.Linear weight W [N][K]
-    void put_linear(GemmWeight& gw, const std::string& wname, const char* bname) {
+    void put_linear(GemmWeight& gw, const std::string& wname, const char* bname, int wide = 0) {
         const Weight& W = h->weights[h->index.at(wname)];
         const int N = (int)W.shape[0], K = (int)W.shape[1];
         std::vector<float> t;
@@ -213,7 +214,7 @@ struct Packer {
         for (int n = 0; n < N; ++n)
             for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W.host[(size_t)n * K + k];
         put(&gw.wt, t);
-        put_tc(gw, t);
+        put_tc(gw, t, wide);
         gw.bias = nullptr;
         if (bname) put(&gw.bias, w(bname));
     }
@@ -226,11 +227,12 @@ struct Packer {
         return x;
     }
     // tcgen05 operand images from the packed Wt [Kpad][ldw] (see TcWeight in gemm.cuh)
-    void put_tc(GemmWeight& gw, const std::vector<float>& t) {
+    void put_tc(GemmWeight& gw, const std::vector<float>& t, int wide = 0) {
         TcWeight& w = gw.tc;
         w.N = gw.N;
         w.K = gw.K;
-        const tc::Tiling tl = tc::choose_tiling(gw.N, gw.K);
+        const tc::Tiling tl = tc::choose_tiling(gw.N, gw.K, wide);
+        w.wide = wide;
         w.ntn = tl.ntn;
         w.nsub = tl.nsub;
         w.BN = tl.BN;
@@ -266,7 +268,7 @@ struct Packer {
         gw.Kpad = round_up(K, kBK);
         gw.ldw = round_up(N, 4);
         gw.bias = nullptr;
-        gw.tc = TcWeight{nullptr, N, K, 0, 0, 0, 0, 0};
+        gw.tc = TcWeight{nullptr, N, K, 0, 0, 0, 0, 0, 0};
         t.assign((size_t)gw.Kpad * gw.ldw, 0.f);
     }
 };
@@ -288,7 +290,7 @@ static void pack_layer(Packer& P, int li) {
         P.put_ln(bw.n2, b + ".norm2", d.C);
         P.put_linear(bw.qkv, b + ".attn.qkv.weight", (b + ".attn.qkv.bias").c_str());
         P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str());
-        P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str());
+        P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str(), 1);
         P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str());
         // relative-position bias gathered to [heads][16][16] (attention.py:190-205, 229-232)
         const std::vector<float>& table = P.w(b + ".attn.relative_position_bias_table");
@@ -662,6 +664,10 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     Bump bp(ws, ws_bytes);
     plan(h, B, W, T, what, bp, c.wk);
     c.L.ln_stats = c.wk.stats;
+#ifdef ESCB_TC_TRACE
+    c.L.trace = h->trace;
+    if (h->trace) cudaMemsetAsync(h->trace, 0, 1024 * 16 * 8, c.L.st);
+#endif
     return ESCB_OK;
 }
 
@@ -1080,6 +1086,16 @@ int escb_profile_end(escb_handle* h, escb_op_stat* stats, int32_t* n) {
     if (e != cudaSuccess) return fail(ESCB_ECUDA, "escb_profile_end: %s", cudaGetErrorString(e));
     return ESCB_OK;
 }
+
+#ifdef ESCB_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int escb_debug_trace(escb_handle* h, unsigned long long* out_host) {
+    if (!h) return -1;
+    if (!h->trace) { cudaMalloc((void**)&h->trace, 1024 * 16 * 8); cudaMemset(h->trace, 0, 1024 * 16 * 8); return 0; }
+    cudaDeviceSynchronize();
+    if (out_host) cudaMemcpy(out_host, h->trace, 1024 * 16 * 8, cudaMemcpyDeviceToHost);
+    return 0;
+}
+#endif
 
 int64_t escb_launch_count(const escb_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
 

@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
 
 static size_t conv3_smem_bytes(int ld) { return (size_t)(kC3F + 2) * ((kC3T + 2) * ld + 4) * sizeof(float); }
 
@@ -18,7 +18,7 @@ void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long 
     L.begin(OP_STFT, 2.0 * B * T * f.win * 2 * f.F, 4.0 * (1.0 * B * Ls + 2.0 * B * T * f.F));
     AStftFrames al{audio, Ls, T, f.hop, f.win / 2};
     EpiRows<false, false> ep{Sf, nullptr, nullptr, 2 * f.F, 0};
-    L.note(GemmLauncher<false, AStftFrames, EpiRows<false, false>, 8>::launch(L.st, al, noln(), f.dft, (long long)B * T, ep));
+    L.note(GemmLauncher<false, AStftFrames, EpiRows<false, false>, 8>::launch(L.st, al, noln(L), f.dft, (long long)B * T, ep));
 }
 
 void op_patch_embed(Launcher& L, const FrontW& f, const float* Sf, int B, int T, int H, int W, float* tok, int ld) {
@@ -34,8 +34,8 @@ void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, i
     L.begin(OP_DEEMBED1, 2.0 * B * H * W * f.de1.N * 25 * f.C0, 4.0 * B * H * W * (f.C0 + f.de1.N));
     AIm2col al{tok, ld, H, W, f.C0};
     EpiDeembed ep{Y1, f.de1.bias, ld, H, W, f.C0, f.pf, f.pt};
-    if (L.tc) L.note(tc::launch<false, AIm2col, EpiDeembed>(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
-    else L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(), f.de1, (long long)B * H * W, ep));
+    if (L.tc) L.note(tc::launch<false, AIm2col, EpiDeembed>(L.st, al, noln(L), f.de1, (long long)B * H * W, ep));
+    else L.note(GemmLauncher<false, AIm2col, EpiDeembed, 9>::launch(L.st, al, noln(L), f.de1, (long long)B * H * W, ep));
     const int Fq = H * f.pf, T2 = W * f.pt;
     const long long total = (long long)B * Fq * T2;
     L.begin(OP_DEEMBED2, 2.0 * total * 2 * 9 * f.C0, 4.0 * total * (f.C0 + 2.0));
@@ -53,7 +53,7 @@ void op_istft(Launcher& L, const FrontW& f, const float* Xf, int B, int T, float
     L.begin(OP_ISTFT, 2.0 * B * nchunks * f.hop * f.nov * 2 * f.F, 4.0 * (2.0 * B * T * f.F + 1.0 * B * nchunks * f.hop));
     AIstft al{Xf, T, 2 * f.F, j0, nchunks};
     EpiIstft ep{audio, f.wsq, T, f.hop, f.nov, j0, nchunks, (long long)f.hop * (T - 1)};
-    L.note(GemmLauncher<false, AIstft, EpiIstft, 5>::launch(L.st, al, noln(), f.idft, (long long)B * nchunks, ep));
+    L.note(GemmLauncher<false, AIstft, EpiIstft, 5>::launch(L.st, al, noln(L), f.idft, (long long)B * nchunks, ep));
 }
 
 void op_transpose(Launcher& L, const float* in, float* out, int B, int R, int C) {

@@ -25,6 +25,7 @@ struct LnParams {
     const float* beta;
     float eps;
     float2* stats;        // [M] (mean, rstd) scratch of the tcgen05 engine's ln_stats_kernel (unused by the SIMT engine)
+    unsigned long long* trace;   // ESCB_TC_TRACE builds: 16 counters of this launch (null otherwise)
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -36,9 +37,9 @@ __device__ __forceinline__ float4 mask4(float4 v, int k, int K) {
     return v;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// L2 prefetch of elements [0, n) of a row, 128 bytes per probe, probes interleaved over `half` in {0, 1}
-__device__ __forceinline__ void prefetch_row(const float* p, int n, int half) {
-    for (int k = half * 32; k < n; k += 64) prefetch_l2(p + k);
+// L2 prefetch of elements [0, n) of a row, 128 bytes per probe, probes interleaved over four threads
+__device__ __forceinline__ void prefetch_row(const float* p, int n, int part) {   // part in 0..3
+    for (int k = part * 32; k < n; k += 128) prefetch_l2(p + k);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -200,6 +201,7 @@ struct TcWeight {
     const float* img;
     int N, K, BN, nsub, ntn, nkb;     // ntn output tiles of nsub sub-tiles of BN columns (tc::choose_tiling)
     int resident;       // the whole n-tile (nkb K blocks) stays in shared memory for the life of a CTA
+    int wide;           // tiled for the 16-epilogue-warp role split (tc::Roles<4>)
 };
 
 struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be null

@@ -70,6 +70,9 @@ struct Launcher {                                    // stream + launch accounti
     bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
+    unsigned long long* trace = nullptr;             // ESCB_TC_TRACE builds: 16 counters per GEMM launch
+    int trace_n = 0;
+    unsigned long long* next_trace() { return trace ? trace + 16 * (size_t)(trace_n++ % 1024) : nullptr; }
     bool open = false;
     // flops / bytes: ALGORITHMIC work of the launch that follows (true dims, no padding, no 3x anything)
     void begin(int op, double flops, double bytes) {

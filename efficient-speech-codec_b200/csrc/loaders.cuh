@@ -22,7 +22,7 @@ struct ARows {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
-    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(r.p, K, half); }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const { prefetch_row(r.p, K, part); }
 };
 
 // Window partition of a [B,H,W,C] token map zero-padded to (Hp,Wp) and cyclically shifted by `shift`
@@ -61,7 +61,7 @@ struct AWindow {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
-    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(r.p, K, half); }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const { prefetch_row(r.p, K, part); }
 };
 
 // PatchMerge gather (scale.py:7-14,104-112): row m = (b, h2, w) is [ x[b,2*h2,w,:] ; x[b,2*h2+1,w,:] ], K = 2C.
@@ -90,7 +90,9 @@ struct AMerge {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
-    __device__ __forceinline__ void prefetch(const Row& r, int K, int half) const { prefetch_row(half ? r.p1 : r.p0, C, 0); }
+    __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const {
+        for (int k = (part >> 1) * 32; k < C; k += 64) prefetch_l2(((part & 1) ? r.p1 : r.p0) + k);
+    }
 };
 
 // Product-VQ frame of the residual enc - dec (csrvq.py:15-17; quantization.py:400-409).  The reference's frame
@@ -283,13 +285,18 @@ struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
     }
     // tcgen05 epilogue: the bias of a column chunk is fetched once (bias4) and added by the caller
     __device__ __forceinline__ float4 bias4(int n) const { return bias ? ldg4(bias + n) : zero4(); }
-    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { fin4(c, n, v, resid4(c, n)); }
+    // split form: the residual is fetched early (resid4, before the accumulator is read) and applied by fin4
+    __device__ __forceinline__ float4 resid4(const Row& c, int n) const {
+        return RES ? *reinterpret_cast<const float4*>(R + c.r + n) : zero4();
+    }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4 r) const {
         if (GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-        if (RES) {
-            const float4 r = *reinterpret_cast<const float4*>(R + c.r + n);
-            v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
-        }
+        if (RES) { v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w; }
         *reinterpret_cast<float4*>(Y + c.y + n) = v;
+    }
+    __device__ __forceinline__ void prefetch(const Row& c, int N) const {
+        if (RES) for (int k = 0; k < N; k += 32) prefetch_l2(R + c.r + k);
     }
 };
 
@@ -316,10 +323,14 @@ struct EpiWindow {
         *reinterpret_cast<float4*>(Y + c.off + n) = v;
     }
     __device__ __forceinline__ float4 bias4(int n) const { return ldg4(bias + n); }
-    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
-        const float4 r = *reinterpret_cast<const float4*>(R + c.off + n);
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { fin4(c, n, v, resid4(c, n)); }
+    __device__ __forceinline__ float4 resid4(const Row& c, int n) const { return *reinterpret_cast<const float4*>(R + c.off + n); }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4 r) const {
         v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
         *reinterpret_cast<float4*>(Y + c.off + n) = v;
+    }
+    __device__ __forceinline__ void prefetch(const Row& c, int N) const {
+        for (int k = 0; k < N; k += 32) prefetch_l2(R + c.off + k);
     }
 };
 
@@ -347,6 +358,9 @@ struct EpiSplit {
     }
     __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
     __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
+    __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4(c, n, v); }
+    __device__ __forceinline__ void prefetch(const Row&, int) const {}
 };
 
 // product-VQ post_process + post_fuse (quantization.py:411-432; csrvq.py:19-21): column n' = (h, o, c) of frame
@@ -375,6 +389,9 @@ struct EpiFrame {
     }
     __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
     __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
+    __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4(c, n, v); }
+    __device__ __forceinline__ void prefetch(const Row&, int) const {}
 };
 
 // conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78):
@@ -402,6 +419,9 @@ struct EpiDeembed {
     __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
         put(c, n, v.x); put(c, n + 1, v.y); put(c, n + 2, v.z); put(c, n + 3, v.w);
     }
+    __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4_nb(c, n, v); }
+    __device__ __forceinline__ void prefetch(const Row&, int) const {}
 };
 
 // overlap-add normalisation + trim of torch.istft: sample s = hop*(j - j0) + n of clip b gets v / envelope, where
@@ -431,6 +451,9 @@ struct EpiIstft {
     }
     __device__ __forceinline__ float4 bias4(int) const { return zero4(); }
     __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { store4(c, n, v); }
+    __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
+    __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4(c, n, v); }
+    __device__ __forceinline__ void prefetch(const Row&, int) const {}
 };
 
 }  // namespace escb

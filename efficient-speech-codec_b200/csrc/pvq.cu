@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
 
 void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz) {
     AFrame al{enc, dec, q.in_freq, W, q.in_dim};
@@ -13,7 +13,7 @@ void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* de
     const long long M = (long long)B * (W / 2);
     L.begin(OP_PVQ_DOWN, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim + 3.0 * q.d));
     // stays on the fp32 SIMT engine: its output feeds the argmin directly (and is no faster on the tensor cores)
-    L.note(GemmLauncher<false, AFrame, EpiRows<false, false>, 3, 6>::launch(L.st, al, noln(), q.down, M, ep));
+    L.note(GemmLauncher<false, AFrame, EpiRows<false, false>, 3, 6>::launch(L.st, al, noln(L), q.down, M, ep));
 }
 
 void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
@@ -22,8 +22,8 @@ void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int 
     EpiFrame ep{out, dec, q.in_freq, W, q.in_dim};
     const long long M = (long long)B * (W / 2);
     L.begin(OP_PVQ_UP, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim) + 24.0 * M);
-    if (L.pvq_tc) L.note(tc::launch<false, ACodes, EpiFrame>(L.st, al, noln(), q.up, M, ep));
-    else L.note(GemmLauncher<false, ACodes, EpiFrame, 8, 9>::launch(L.st, al, noln(), q.up, M, ep));
+    if (L.pvq_tc) L.note(tc::launch<false, ACodes, EpiFrame>(L.st, al, noln(L), q.up, M, ep));
+    else L.note(GemmLauncher<false, ACodes, EpiFrame, 8, 9>::launch(L.st, al, noln(L), q.up, M, ep));
 }
 
 template <int D>

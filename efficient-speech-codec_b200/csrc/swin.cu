@@ -5,8 +5,8 @@
 
 namespace escb {
 
-static inline LnParams lnp(const Launcher& L, const LnW& w) { return LnParams{w.g, w.b, kLnEps, L.ln_stats}; }
-static inline LnParams noln() { return LnParams{nullptr, nullptr, 0.f, nullptr}; }
+static inline LnParams lnp(Launcher& L, const LnW& w) { return LnParams{w.g, w.b, kLnEps, L.ln_stats, L.next_trace()}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
 
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq) {
     L.begin(OP_QKV, 2.0 * M * w.qkv.N * w.qkv.K, 4.0 * (1.0 * M * w.qkv.K + 1.0 * M * w.qkv.N));
@@ -21,15 +21,15 @@ void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const floa
     L.begin(OP_PROJ, 2.0 * M * w.proj.N * w.proj.K, 4.0 * 3.0 * M * w.proj.K);
     ARows al{att, lda};
     EpiWindow ep{y, resid, w.proj.bias, ld, g};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow>(L.st, al, noln(), w.proj, M, ep));
-    else L.note(GemmLauncher<false, ARows, EpiWindow, 3, 5, 6, 8, 9>::launch(L.st, al, noln(), w.proj, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow>(L.st, al, noln(L), w.proj, M, ep));
+    else L.note(GemmLauncher<false, ARows, EpiWindow, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.proj, M, ep));
 }
 
 void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh) {
     L.begin(OP_MLP1, 2.0 * M * w.fc1.N * w.fc1.K, 4.0 * M * (w.fc1.K + w.fc1.N));
     ARows al{x, ld};
     EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
-    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, true>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
 }
 
@@ -37,8 +37,8 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
     L.begin(OP_MLP2, 2.0 * M * w.fc2.N * w.fc2.K, 4.0 * M * (w.fc2.K + 2.0 * w.fc2.N));
     ARows al{hid, ldh};
     EpiRows<false, true> ep{x, w.fc2.bias, x, ld, ld};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>>(L.st, al, noln(), w.fc2, M, ep));
-    else L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(), w.fc2, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>>(L.st, al, noln(L), w.fc2, M, ep));
+    else L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.fc2, M, ep));
 }
 
 void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {

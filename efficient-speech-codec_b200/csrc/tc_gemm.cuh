@@ -8,21 +8,24 @@
 // (the dropped lo*lo term is 2^-22 relative).  Weights are split once at escb_finalize(); activations are split
 // by the A-producer warps after the fused gather / LayerNorm.
 //
-// One persistent CTA per SM (576 threads), warp-specialised, looping over 128 x BN output tiles:
-//   warps 0-7   epilogue : tcgen05.ld the finished accumulator (one TMEM lane quadrant x one column half per warp),
+// One persistent CTA per SM (832 threads), warp-specialised, looping over 128 x NT output tiles (NT <= 512):
+//   warps 0-7   epilogue : tcgen05.ld a finished sub-tile (one TMEM lane quadrant x one column half per warp),
 //                          transpose 32x16 chunks through a swizzled smem staging tile so that global stores and
 //                          residual loads are 64-byte row segments, apply bias / GELU / residual / scatter functor;
-//   warps 8-15  producer : gather the logical A rows (window partition + cyclic shift, frequency-row pairing,
+//   warps 8-23  producer : gather the logical A rows (window partition + cyclic shift, frequency-row pairing,
 //                          im2col ... loaders.cuh), LayerNorm, cvt.rna.tf32 split, write the hi / lo images of a
-//                          32-wide K block in the 128-byte-swizzled K-major layout into a 3-slot ring; the next
-//                          tile is prefetched into L2 and its LayerNorm statistics are computed while the tensor
-//                          core drains the ring;
-//   warp 16     MMA      : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 3 per
-//                          k-step; tcgen05.commit releases the A slot / weight slot and publishes the accumulator;
-//   warp 17     weights  : pre-swizzled [hi | lo] weight images, ONE cp.async.bulk (SASS UBLKCP) per K block.
-//                          Layers whose whole n-tile fits (nkb * BN * 256 B <= ~108 KB) keep it RESIDENT in smem
-//                          for the life of the CTA; the others stream it through a 2..8 slot ring.
-// Two 256-column TMEM accumulators alternate between tiles, so the epilogue of tile t overlaps the MMAs of t+1.
+//                          32-wide K block in the 128-byte-swizzled K-major layout into a 3-slot ring.  The
+//                          (tile, K block) jobs form one flat stream with the loads of four jobs in flight per
+//                          thread and the following tile prefetched into L2;
+//   warp 24     MMA      : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 3 per
+//                          k-step and sub-tile; tcgen05.commit releases the A slot / weight slot and publishes
+//                          each sub-tile's accumulator;
+//   warp 25     weights  : pre-swizzled [hi | lo] weight images, ONE cp.async.bulk (SASS UBLKCP) per (K block,
+//                          sub-tile).  Layers whose whole n-tile fits keep it RESIDENT in smem for the life of
+//                          the CTA; the others stream it through a 2..8 slot ring.
+// An output tile is nsub sub-tiles of BN columns, each with its own TMEM region and full/empty barriers, so the
+// A operand is produced ONCE for up to 512 output columns while the epilogue of a sub-tile overlaps the MMAs of
+// the next ones (and of the next tile when two tiles fit the 512 columns).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,21 +37,35 @@ namespace tc {
 
 constexpr int BM = 128;               // UMMA M
 constexpr int KB = 32;                // tf32 per 128-byte swizzle row = one K block
-constexpr int EPI_WARPS = 8;
-constexpr int PROD_WARPS = 8;
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;
-constexpr int NA = 3;                 // A ring slots
+constexpr int WARPS = 26;              // 24 epilogue + producer warps, 1 MMA warp, 1 weight-loader warp
+constexpr int THREADS = WARPS * 32;
 constexpr int MAX_NB = 8;             // weight ring slots (upper bound)
 constexpr int MAX_BN = 208;
 constexpr int A_SLOT = 2 * BM * 128;  // hi + lo images of one A block
-constexpr int ACC_STRIDE = 256;       // TMEM columns between the two accumulators
-constexpr int STG_BYTES = EPI_WARPS * 32 * 16 * 4;
-constexpr int CTX_BYTES = EPI_WARPS * 32 * 16;
-constexpr int NBARS = 2 * NA + 2 * MAX_NB + 4;
-constexpr int TAIL_BYTES = STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4 + NBARS * 8 + 16;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_REG = 8;            // accumulator regions (sub-tiles in flight)
 constexpr int SMEM_MAX = 232448;      // 227 KB opt-in limit per CTA
-constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
+constexpr int MAX_NA = 3;
+constexpr int NBARS = 2 * MAX_NA + 2 * MAX_NB + 2 * MAX_REG;
+
+// Role split: E epilogue warps per TMEM lane quadrant.  E = 2: 8 epilogue + 16 producer warps, 3 A slots (the
+// default); E = 4: 16 epilogue + 8 producer warps, 2 A slots, for the GELU GEMM (small K, wide N) whose erf
+// epilogue would otherwise stall the tensor pipe.
+template <int E>
+struct Roles {
+    static constexpr int EPI_WARPS = 4 * E;
+    static constexpr int PROD_WARPS = 24 - EPI_WARPS;
+    static constexpr int PROD_THREADS = PROD_WARPS * 32;
+    static constexpr int RPT = 32 / PROD_WARPS;            // rows per producer thread: 2 or 4
+    static constexpr int ROW_STEP = 4 * PROD_WARPS;        // distance between a thread's rows
+    static constexpr int DEPTH = 8 / RPT;                  // producer jobs with loads in flight
+    static constexpr int NA = E == 4 ? 2 : 3;              // A ring slots
+    static constexpr int STG_BYTES = EPI_WARPS * 32 * 16 * 4;
+    static constexpr int CTX_BYTES = EPI_WARPS * 32 * 16;
+    static constexpr int TAIL_BYTES = STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4 + NBARS * 8 + 16;
+    static constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
+};
+inline int b_budget(int wide) { return wide ? Roles<4>::B_BUDGET : Roles<2>::B_BUDGET; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,9 +89,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             ".reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
         if (done) break;
-        if (++spins > 400000u) __trap();
+        if (++spins > 4000000u) __trap();
     }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -140,16 +157,31 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi.w = tf32_rna(v.w); lo.w = tf32_rna(v.w - hi.w);
 }
 
-template <bool LN, class AL, class EP>
+#ifdef ESCB_TC_TRACE
+#define TC_T0(v) const long long v = clock64()
+#define TC_ACC(slot, v) tr[slot] += clock64() - (v)
+#else
+#define TC_T0(v)
+#define TC_ACC(slot, v)
+#endif
+
+template <bool LN, class AL, class EP, int E>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
                const int NB, const int resident) {
     static_assert(sizeof(typename EP::Row) <= 16, "epilogue row context must fit 16 bytes");
+    using R = Roles<E>;
+    constexpr int EPI_WARPS = R::EPI_WARPS, PROD_WARPS = R::PROD_WARPS, PROD_THREADS = R::PROD_THREADS;
+    constexpr int RPT = R::RPT, ROW_STEP = R::ROW_STEP, DEPTH = R::DEPTH, NA = R::NA;
+    constexpr int STG_BYTES = R::STG_BYTES, CTX_BYTES = R::CTX_BYTES;
     extern __shared__ uint8_t smem_raw[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = w.K, BN = w.BN, nkb = w.nkb, ntn = w.ntn, nsub = w.nsub;
     const int NT = BN * nsub;                             // columns of one output tile
+    // accumulator regions of BN columns form a ring over TMEM: sub-tile number g (counted over this CTA's tiles)
+    // lives in region g % nreg, so whenever nreg > nsub the next tile starts while this one is being drained
+    const int nreg = TMEM_COLS / BN < MAX_REG ? TMEM_COLS / BN : MAX_REG;
 
     // 1024-byte alignment for the 128-byte swizzle atoms, as an offset so the pointers stay in the shared window
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -162,128 +194,173 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
     int* eok_all = reinterpret_cast<int*>(tail + STG_BYTES + CTX_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
-    const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * NA, b_full = a_empty + 8 * NA,
-                   b_empty = b_full + 8 * MAX_NB, acc_full = b_empty + 8 * MAX_NB, acc_empty = acc_full + 16;
+    const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * MAX_NA, b_full = a_empty + 8 * MAX_NA,
+                   b_empty = b_full + 8 * MAX_NB, acc_full = b_empty + 8 * MAX_NB, acc_empty = acc_full + 8 * MAX_REG;
 
-    if (warp == EPI_WARPS + PROD_WARPS) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (warp == EPI_WARPS + PROD_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)TMEM_COLS);
     if (tid == THREADS - 32) {
         for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, PROD_THREADS); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < MAX_NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, EPI_WARPS * 32); }
+        for (int i = 0; i < MAX_REG; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, EPI_WARPS * 32); }
         fence_barrier_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+#ifdef ESCB_TC_TRACE
+    long long tr[4] = {0, 0, 0, 0};
+    const long long tr_start = clock64();
+#endif
 
     if (warp < EPI_WARPS) {
         // ======================================================================================== epilogue
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;          // TMEM lane quadrant, column share (of E)
         float* stg = stg_all + warp * (32 * 16);
         typename EP::Row* ectx = ectx_all + warp * 32;
         int* eok = eok_all + warp * 32;
-        const int nch = NT >> 4, N = w.N;
+        const int nch = BN >> 4, N = w.N;
         const int rr = lane >> 2, c4 = lane & 3;           // transposed side: rows rr + 8 i, 16-byte chunk c4
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1;
+        uint32_t reg = 0, rphase = 0;                      // accumulator region of the next sub-tile and its phase
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = (long long)(tile / ntn) * BM + q * 32 + lane;
             const int n0 = (tile % ntn) * NT;
-            typename EP::Row er;
-            int ok = m < M;
-            if (ok) ok = ep.row(m, er) ? 1 : 0;
-            __syncwarp();
-            ectx[lane] = er;
-            eok[lane] = ok;
-            mbar_wait(acc_full + 8 * buf, (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tbase = tmem + buf * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-            for (int ch = half; ch < nch; ch += 2) {
-                float v[16];
-                tmem_ld16(tbase + (uint32_t)(ch * 16), v);
-                __syncwarp();                              // previous chunk's reads of the staging tile are done
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            {
+                typename EP::Row er;
+                int ok = m < M;
+                if (ok) ok = ep.row(m, er) ? 1 : 0;
                 __syncwarp();
-                const int n = n0 + ch * 16 + c4 * 4;
-                const bool full4 = n + 3 < N;
-                const float4 b4 = full4 ? ep.bias4(n) : zero4();
+                ectx[lane] = er;
+                eok[lane] = ok;
+                __syncwarp();
+            }
+            if (part == 0 && tile + (int)gridDim.x < ntiles) {   // residual rows of the next tile -> L2
+                const long long mn = (long long)((tile + gridDim.x) / ntn) * BM + q * 32 + lane;
+                typename EP::Row pr;
+                if (mn < M && ep.row(mn, pr)) ep.prefetch(pr, N);
+            }
+            typename EP::Row cr[4];                        // contexts of this lane's four transposed-side rows
+            unsigned okm = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rr + 8 * i;
-                    if (!eok[r] || n >= N) continue;
-                    float4 o = *reinterpret_cast<const float4*>(stg + r * 16 + ((c4 ^ ((r >> 1) & 3)) << 2));
-                    const typename EP::Row cr = ectx[r];
+            for (int i = 0; i < 4; ++i) {
+                cr[i] = ectx[rr + 8 * i];
+                if (eok[rr + 8 * i]) okm |= 1u << i;
+            }
+            for (int sub = 0; sub < nsub; ++sub) {
+                { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
+                tc_fence_after();
+                const uint32_t tbase = tmem + reg * BN + ((uint32_t)(q * 32) << 16);
+                for (int ch = part; ch < nch; ch += E) {
+                    // bias and residual of this lane's four row segments are requested before the accumulator is
+                    // read, so their latency (L2 hits: the rows were prefetched a tile ahead) overlaps the staging
+                    const int n = n0 + sub * BN + ch * 16 + c4 * 4;
+                    const bool full4 = n + 3 < N;
+                    float4 b4 = zero4(), res[4];
                     if (full4) {
-                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                        ep.store4_nb(cr, n, o);
-                    } else {
-                        ep.store(cr, n, o.x);
-                        if (n + 1 < N) ep.store(cr, n + 1, o.y);
-                        if (n + 2 < N) ep.store(cr, n + 2, o.z);
+                        b4 = ep.bias4(n);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) res[i] = ((okm >> i) & 1u) ? ep.resid4(cr[i], n) : zero4();
+                    }
+                    float v[16];
+                    tmem_ld16(tbase + (uint32_t)(ch * 16), v);
+                    __syncwarp();                          // previous chunk's reads of the staging tile are done
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (!((okm >> i) & 1u) || n >= N) continue;
+                        const int r = rr + 8 * i;
+                        float4 o = *reinterpret_cast<const float4*>(stg + r * 16 + ((c4 ^ ((r >> 1) & 3)) << 2));
+                        if (full4) {
+                            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                            ep.fin4(cr[i], n, o, res[i]);
+                        } else {
+                            ep.store(cr[i], n, o.x);
+                            if (n + 1 < N) ep.store(cr[i], n + 1, o.y);
+                            if (n + 2 < N) ep.store(cr[i], n + 2, o.z);
+                        }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(acc_empty + 8 * reg);
+                if (++reg == (uint32_t)nreg) { reg = 0; rphase ^= 1; }
             }
-            tc_fence_before();
-            mbar_arrive(acc_empty + 8 * buf);
         }
     } else if (warp < EPI_WARPS + PROD_WARPS) {
         // ======================================================================================== A producer
-        // 16-byte chunk c of the 128-byte K-block row, rows r0 + 32 i (8 consecutive lanes share a row).  The
-        // (tile, K block) jobs of this CTA form one flat stream; the loads of job j+2 are issued before job j is
-        // converted, so two K blocks of global loads (plus the L2 prefetch of the following tile) are always in
-        // flight and tile boundaries cost nothing.  LayerNorm statistics come from ln_stats_kernel.
+        // 16-byte chunk c of the 128-byte K-block row, rows r0 and r0 + 64 (8 consecutive lanes share a row).  The
+        // (tile, K block) jobs of this CTA form one flat stream; the loads of job j + DEPTH are issued right after
+        // job j is converted, so DEPTH K blocks of global loads (plus the L2 prefetch of the following tile) are
+        // always in flight and tile boundaries cost nothing.  LayerNorm statistics come from ln_stats_kernel.
         const int pt = tid - EPI_WARPS * 32;
         const int c = pt & 7, r0 = pt >> 3;
-        typename AL::Row myrow[4];
-        unsigned cur_vm = 0;
-        long long cur_m0 = 0;
+        struct Job { float4 a[RPT]; int k; unsigned m0, vm; };
+        typename AL::Row myrow[RPT];
+        unsigned cur_vm = 0, cur_m0 = 0;
         int ld_tile = blockIdx.x, ld_kb = 0;
 
-        auto issue = [&](float4 (&a)[4], float2 (&st)[4], unsigned& vm, int& kk) -> bool {
+        auto issue = [&](Job& j) -> bool {
             if (ld_tile >= ntiles) return false;
             if (ld_kb == 0) {
-                cur_m0 = (long long)(ld_tile / ntn) * BM;
+                TC_T0(ti_);
+                cur_m0 = (unsigned)(ld_tile / ntn) * BM;
                 cur_vm = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    al.init(cur_m0 + r0 + 32 * i, M, myrow[i]);
+                for (int i = 0; i < RPT; ++i) {
+                    al.init((long long)cur_m0 + r0 + ROW_STEP * i, M, myrow[i]);
                     if (al.valid(myrow[i])) cur_vm |= 1u << i;
                 }
                 const int next = ld_tile + gridDim.x;
-                if (next < ntiles) {                       // pull the following tile's rows into L2 (two threads per row)
+                if (next < ntiles && pt < 512) {           // pull the following tile's rows into L2 (four threads per row)
                     typename AL::Row pr;
-                    al.init((long long)(next / ntn) * BM + (pt >> 1), M, pr);
-                    if (al.valid(pr)) al.prefetch(pr, K, pt & 1);
+                    if (PROD_THREADS >= 512) {
+                        al.init((long long)(next / ntn) * BM + (pt >> 2), M, pr);
+                        if (al.valid(pr)) al.prefetch(pr, K, pt & 3);
+                    } else {                               // 256 producer threads: two rows each
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            al.init((long long)(next / ntn) * BM + (pt >> 2) + 64 * h, M, pr);
+                            if (al.valid(pr)) al.prefetch(pr, K, pt & 3);
+                        }
+                    }
                 }
+                TC_ACC(3, ti_);
             }
             const int k = ld_kb * KB + c * 4;
-            kk = k;
-            vm = cur_vm;
+            j.k = k;
+            j.vm = cur_vm;
+            j.m0 = cur_m0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool on = ((cur_vm >> i) & 1u) && k < K;
-                a[i] = on ? al.load4(myrow[i], k, K) : zero4();
-                if (LN) st[i] = on ? __ldg(ln.stats + cur_m0 + r0 + 32 * i) : make_float2(0.f, 0.f);
-            }
+            for (int i = 0; i < RPT; ++i)
+                j.a[i] = (((cur_vm >> i) & 1u) && k < K) ? al.load4(myrow[i], k, K) : zero4();
             if (++ld_kb == nkb) { ld_kb = 0; ld_tile += gridDim.x; }
             return true;
         };
 
         uint32_t slot = 0, phase = 0;                     // ring position of the next K block
-        auto convert = [&](const float4 (&a)[4], const float2 (&st)[4], const unsigned vm, const int k) {
+        auto convert = [&](const Job& j) {
+            const int k = j.k;
             float4 g = zero4(), be = zero4();
-            if (LN && k < K) { g = ldg4(ln.gamma + k); be = ldg4(ln.beta + k); }
-            mbar_wait(a_empty + 8 * slot, phase ^ 1);
+            float2 st[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) st[i] = make_float2(0.f, 0.f);
+            if (LN && k < K) {
+                g = ldg4(ln.gamma + k);
+                be = ldg4(ln.beta + k);
+#pragma unroll
+                for (int i = 0; i < RPT; ++i)
+                    if ((j.vm >> i) & 1u) st[i] = __ldg(ln.stats + (j.m0 + r0 + ROW_STEP * i));
+            }
+            { TC_T0(t_); mbar_wait(a_empty + 8 * slot, phase ^ 1); TC_ACC(0, t_); }
             uint8_t* dst = smem + slot * A_SLOT;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 32 * i;
-                float4 v = a[i];
-                if (LN && k < K && ((vm >> i) & 1u)) {
+            for (int i = 0; i < RPT; ++i) {
+                const int r = r0 + ROW_STEP * i;
+                float4 v = j.a[i];
+                if (LN && k < K && ((j.vm >> i) & 1u)) {
                     const float mean = st[i].x, rstd = st[i].y;
                     v.x = (v.x - mean) * rstd * g.x + be.x;
                     v.y = (v.y - mean) * rstd * g.y + be.y;
@@ -302,41 +379,39 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             if (++slot == NA) { slot = 0; phase ^= 1; }
         };
 
-        float4 a0[4], a1[4];
-        float2 s0[4], s1[4];
-        unsigned vm0 = 0, vm1 = 0;
-        int k0 = 0, k1 = 0;
-        bool h0 = issue(a0, s0, vm0, k0);
-        bool h1 = h0 && issue(a1, s1, vm1, k1);
-        while (h0) {
-            convert(a0, s0, vm0, k0);
-            h0 = issue(a0, s0, vm0, k0);
-            if (!h1) break;
-            convert(a1, s1, vm1, k1);
-            h1 = h0 && issue(a1, s1, vm1, k1);
+        Job jobs[DEPTH];
+        bool have[DEPTH];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) have[d] = issue(jobs[d]);
+        while (have[0]) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                if (have[d]) {
+                    { TC_T0(t_); convert(jobs[d]); TC_ACC(1, t_); }
+                    { TC_T0(t_); have[d] = issue(jobs[d]); TC_ACC(2, t_); }
+                }
+            }
         }
     } else if (warp == EPI_WARPS + PROD_WARPS) {
         // ======================================================================================== MMA issuer
         const uint32_t idesc = make_idesc(BN);
-        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const uint32_t buf = it & 1;
-            mbar_wait(acc_empty + 8 * buf, ((it >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem + buf * ACC_STRIDE;
+        uint32_t aslot = 0, aphase = 0, bslot = 0, bphase = 0, reg0 = 0, rphase0 = 0;   // reg0: region of sub-tile 0
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(a_full + 8 * aslot, aphase);
+                { TC_T0(t_); mbar_wait(a_full + 8 * aslot, aphase); TC_ACC(0, t_); }
                 int rem = K - kb * KB;
                 if (rem > KB) rem = KB;
                 const int ksteps = (rem + 7) >> 3;
                 const uint64_t a_hi = make_desc(sA + aslot * A_SLOT), a_lo = make_desc(sA + aslot * A_SLOT + BM * 128);
+                uint32_t reg = reg0, rphase = rphase0;
                 for (int sub = 0; sub < nsub; ++sub) {
+                    if (kb == 0) { TC_T0(t_); mbar_wait(acc_empty + 8 * reg, rphase ^ 1); TC_ACC(1, t_); }   // the epilogue drained this region
                     const uint32_t bs = resident ? (uint32_t)(kb * nsub + sub) : bslot;
-                    mbar_wait(b_full + 8 * bs, resident ? 0u : bphase);
+                    { TC_T0(t_); mbar_wait(b_full + 8 * bs, resident ? 0u : bphase); TC_ACC(2, t_); }
                     tc_fence_after();
                     if (lane == 0) {
                         const uint64_t b_hi = make_desc(sB + bs * b_stage), b_lo = make_desc(sB + bs * b_stage + b_img);
-                        const uint32_t d_sub = d_tmem + (uint32_t)(sub * BN);
+                        const uint32_t d_sub = tmem + reg * BN;
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes >> 4 inside the swizzle row
                             umma_tf32(d_sub, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);
@@ -344,15 +419,15 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                             umma_tf32(d_sub, a_hi + adv, b_hi + adv, idesc, 1u);
                         }
                         if (!resident) umma_commit(b_empty + 8 * bs);
-                        if (sub + 1 == nsub) {
-                            umma_commit(a_empty + 8 * aslot);
-                            if (kb + 1 == nkb) umma_commit(acc_full + 8 * buf);
-                        }
+                        if (kb + 1 == nkb) umma_commit(acc_full + 8 * reg);
+                        if (sub + 1 == nsub) umma_commit(a_empty + 8 * aslot);
                     }
                     __syncwarp();
                     if (!resident && ++bslot == (uint32_t)NB) { bslot = 0; bphase ^= 1; }
+                    if (++reg == (uint32_t)nreg) { reg = 0; rphase ^= 1; }
                 }
                 if (++aslot == NA) { aslot = 0; aphase ^= 1; }
+                if (kb + 1 == nkb) { reg0 = reg; rphase0 = rphase; }
             }
         }
     } else {
@@ -372,7 +447,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                     const int nt = tile % ntn;
                     for (int j = 0; j < nkb * nsub; ++j) {
-                        mbar_wait(b_empty + 8 * bslot, bphase ^ 1);
+                        { TC_T0(t_); mbar_wait(b_empty + 8 * bslot, bphase ^ 1); TC_ACC(0, t_); }
                         mbar_expect_tx(b_full + 8 * bslot, b_stage);
                         bulk_g2s(sB + bslot * b_stage, wimg + ((size_t)nt * nkb * nsub + j) * b_stage, b_stage, b_full + 8 * bslot);
                         if (++bslot == (uint32_t)NB) { bslot = 0; bphase ^= 1; }
@@ -383,11 +458,24 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         __syncwarp();
     }
 
+#ifdef ESCB_TC_TRACE
+    if (ln.trace && lane == 0) {
+        // slots: 0 role total | epilogue: 1 wait acc_full | producer: 2 wait a_empty, 3 convert (incl. wait), 4 issue
+        //        | mma: 5 wait a_full, 6 wait acc_empty, 7 wait b_full | loader: 8 wait b_empty | 9.. role totals
+        const long long total = clock64() - tr_start;
+        unsigned long long* t = ln.trace;
+        if (warp == 0) { atomicAdd(t + 1, (unsigned long long)tr[0]); atomicAdd(t + 9, (unsigned long long)total); atomicAdd(t + 13, 1ull); }
+        if (warp == EPI_WARPS) { atomicAdd(t + 2, (unsigned long long)tr[0]); atomicAdd(t + 3, (unsigned long long)tr[1]); atomicAdd(t + 4, (unsigned long long)tr[2]); atomicAdd(t + 10, (unsigned long long)total); atomicAdd(t + 12, (unsigned long long)tr[3]); }
+        if (warp == EPI_WARPS + PROD_WARPS) { atomicAdd(t + 5, (unsigned long long)tr[0]); atomicAdd(t + 6, (unsigned long long)tr[1]); atomicAdd(t + 7, (unsigned long long)tr[2]); atomicAdd(t + 11, (unsigned long long)total); }
+        if (warp == EPI_WARPS + PROD_WARPS + 1) { atomicAdd(t + 8, (unsigned long long)tr[0]); }
+        if (tid == 0 && blockIdx.x == 0) { t[14] = (unsigned long long)ntiles; t[15] = ((unsigned long long)w.N << 40) | ((unsigned long long)w.K << 20) | ((unsigned long long)w.BN << 8) | ((unsigned long long)w.nsub << 4) | (unsigned long long)w.resident; }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == EPI_WARPS + PROD_WARPS) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512u);
+        tmem_dealloc(tmem, (uint32_t)TMEM_COLS);
     }
 }
 
@@ -443,28 +531,29 @@ inline cudaError_t launch_ln_stats(cudaStream_t st, const AL& al, long long M, i
 }
 
 // Tiling of one weight, decided at pack time (api.cu put_tc): N is cut into ntn output tiles of nsub sub-tiles of
-// BN columns each (BN = the UMMA N and the granularity of the weight ring; nsub * BN <= 256 TMEM columns).  The
-// A operand is produced once per output tile, so wide tiles save producer work and L2 reads; the cost model is
-// L2 traffic per m-tile and K block (units of 256 bytes: 64 per A production, BN per streamed weight stage)
-// against tensor time (6 clocks per column ~ 0.94 units).
+// BN columns each (BN = the UMMA N and the granularity of the weight ring; nsub * BN <= 512 TMEM columns).  The
+// A operand is produced once per output tile (~100 columns worth of tensor time per K block), so the chooser
+// takes the fewest n-tiles, then the least column padding, preferring resident weights and a >= 3 slot ring.
 struct Tiling { int BN, nsub, ntn, nkb, resident; };
 
-inline Tiling choose_tiling(int N, int K) {
+inline Tiling choose_tiling(int N, int K, int wide) {
+    const long long B_BUDGET = b_budget(wide);
     Tiling best{0, 0, 0, 0, 0};
     double best_cost = 1e30;
     const int nkb = (K + KB - 1) / KB;
     for (int ntn = 1; ntn <= 64; ++ntn)
-        for (int nsub = 1; nsub <= 4; ++nsub) {
+        for (int nsub = 1; nsub <= MAX_REG; ++nsub) {
             const int bn = (((N + ntn * nsub - 1) / (ntn * nsub)) + 15) / 16 * 16;
-            if (bn > (nsub == 1 ? MAX_BN : 128) || bn * nsub > ACC_STRIDE) continue;
+            if (bn > (nsub == 1 ? MAX_BN : 128) || bn * nsub > TMEM_COLS) continue;
             if (bn < 48 && ntn * nsub > 1) continue;
             const long long stage = (long long)bn * 256;
             const bool res = stage * nkb * nsub <= B_BUDGET && nkb * nsub <= MAX_NB;
             const int nb = res ? nkb * nsub : (int)(B_BUDGET / stage);
-            if (!res && nb < 3 && nkb * nsub > 2) continue;
+            if (!res && nb < 2) continue;
             const double padn = (double)bn * nsub * ntn;
-            const double l2 = 64.0 * ntn + (res ? 0.0 : padn), mma = 0.94 * padn;
-            const double cost = (l2 > mma ? l2 : mma) + 0.1 * (l2 + padn) + (bn < 64 ? 0.3 * padn : 0.0);
+            const int nreg = TMEM_COLS / bn < MAX_REG ? TMEM_COLS / bn : MAX_REG;
+            const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + (!res && nb < 3 ? 0.2 : 0.0) + (nreg <= nsub ? 0.15 : 0.0)) +
+                                96.0 * ntn + 4.0 * nsub;
             if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0}; }
         }
     return best;
@@ -480,33 +569,41 @@ inline int sm_count() {
     return n;
 }
 
-template <bool LN, class AL, class EP>
-inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
-    const TcWeight& w = gw.tc;
-    if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
-    if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
+template <bool LN, class AL, class EP, int E>
+inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, const TcWeight& w, long long M, const EP& ep) {
+    using R = Roles<E>;
     static bool configured = false;     // per instantiation
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (LN) {
-        if (!ln.stats) return cudaErrorInvalidValue;
-        const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
-        if (e != cudaSuccess) return e;
-    }
     const long long stage = (long long)w.BN * 256;
-    const int NB = w.resident ? w.nkb * w.nsub : (int)(B_BUDGET / stage < MAX_NB ? B_BUDGET / stage : MAX_NB);
-    const size_t smem = 1024 + (size_t)NA * A_SLOT + (size_t)NB * stage + TAIL_BYTES;
+    const int NB = w.resident ? w.nkb * w.nsub : (int)(R::B_BUDGET / stage < MAX_NB ? R::B_BUDGET / stage : MAX_NB);
+    const size_t smem = 1024 + (size_t)R::NA * A_SLOT + (size_t)NB * stage + R::TAIL_BYTES;
     const long long ntm = (M + BM - 1) / BM;
     const long long ntiles = ntm * w.ntn;
     if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     long long grid = sm_count();
     if (w.resident) grid = grid / w.ntn * w.ntn;       // a resident CTA serves one n-tile
     if (grid > ntiles) grid = ntiles;
-    tc_gemm_kernel<LN, AL, EP><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident);
+    tc_gemm_kernel<LN, AL, EP, E><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident);
     return cudaGetLastError();
+}
+
+// WIDE selects the 16-epilogue-warp role split (the weight must have been tiled with choose_tiling(.., wide = 1)).
+template <bool LN, class AL, class EP, bool WIDE = false>
+inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
+    const TcWeight& w = gw.tc;
+    if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
+    if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
+    if ((w.wide != 0) != WIDE) return cudaErrorInvalidValue;
+    if (LN) {
+        if (!ln.stats) return cudaErrorInvalidValue;
+        const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_e<LN, AL, EP, WIDE ? 4 : 2>(st, al, ln, w, M, ep);
 }
 
 }  // namespace tc
