@@ -208,15 +208,34 @@ struct Packer {
     // Wt[k][n] = W[n][k] for a reference nn.Linear weight W [N][K]
     void put_linear(GemmWeight& gw, const std::string& wname, const char* bname, int wide = 0) {
         const Weight& W = h->weights[h->index.at(wname)];
-        const int N = (int)W.shape[0], K = (int)W.shape[1];
+        put_matrix(gw, W.host.data(), (int)W.shape[0], (int)W.shape[1], bname ? &w(bname) : nullptr, wide);
+    }
+    // W [N][K] row-major (nn.Linear layout), optional bias [N]
+    void put_matrix(GemmWeight& gw, const float* W, int N, int K, const std::vector<float>* bias, int wide = 0) {
         std::vector<float> t;
         init_gemm(gw, N, K, t);
         for (int n = 0; n < N; ++n)
-            for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W.host[(size_t)n * K + k];
+            for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W[(size_t)n * K + k];
         put(&gw.wt, t);
         put_tc(gw, t, wide);
         gw.bias = nullptr;
-        if (bname) put(&gw.bias, w(bname));
+        if (bias) put(&gw.bias, *bias);
+    }
+    // qkv projection with its output columns laid out [3][heads][hdp] (internal.h head_pad): rows of the reference
+    // weight (3C, C) are moved to n' = (part*heads + h)*hdp + d, padding rows and their bias are zero
+    void put_qkv(GemmWeight& gw, const std::string& wname, const std::string& bname, int C, int heads) {
+        const std::vector<float>& W = w(wname);
+        const std::vector<float>& B = w(bname);
+        const int hd = C / heads, hdp = head_pad(hd), Np = 3 * heads * hdp;
+        std::vector<float> Wp((size_t)Np * C, 0.f), Bp((size_t)Np, 0.f);
+        for (int part = 0; part < 3; ++part)
+            for (int hh = 0; hh < heads; ++hh)
+                for (int d = 0; d < hd; ++d) {
+                    const int n = part * C + hh * hd + d, np = (part * heads + hh) * hdp + d;
+                    memcpy(&Wp[(size_t)np * C], &W[(size_t)n * C], (size_t)C * sizeof(float));
+                    Bp[np] = B[n];
+                }
+        put_matrix(gw, Wp.data(), Np, C, &Bp);
     }
     static float tf32_rna(float x) {           // cvt.rna.tf32.f32: nearest, ties away, 10 mantissa bits kept
         uint32_t u;
@@ -280,6 +299,7 @@ static void pack_layer(Packer& P, int li) {
     lw.C = d.C;
     lw.heads = d.heads;
     lw.hd = d.C / d.heads;
+    lw.hdp = head_pad(lw.hd);
     lw.depth = h->cfg.swin_depth;
     lw.scale = d.scale;
     lw.out_dim = d.out_dim;
@@ -288,7 +308,7 @@ static void pack_layer(Packer& P, int li) {
         BlockW& bw = lw.blk[j];
         P.put_ln(bw.n1, b + ".norm1", d.C);
         P.put_ln(bw.n2, b + ".norm2", d.C);
-        P.put_linear(bw.qkv, b + ".attn.qkv.weight", (b + ".attn.qkv.bias").c_str());
+        P.put_qkv(bw.qkv, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
         P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str());
         P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str(), 1);
         P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str());
@@ -482,7 +502,12 @@ static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp
         const int C = h->lev[l].C, H = h->lev[l].H, Hp = round_up(H, 4);
         const size_t M = (size_t)B * H * W, Mw = (size_t)B * Hp * Wp;
         max_tok = std::max(max_tok, M * ldc(C));
-        max_qkv = std::max(max_qkv, Mw * ldc(3 * C));
+        int wq = ldc(3 * C);                  // widest head-padded qkv row among the layers working at this level
+        for (int li = 0; li < 2 * L; ++li) {
+            const LayerDesc d = layer_desc(h, li);
+            if (d.C == C) wq = std::max(wq, 3 * d.heads * head_pad(C / d.heads));
+        }
+        max_qkv = std::max(max_qkv, Mw * (size_t)wq);
         max_att = std::max(max_att, Mw * ldc(C));
         max_hid = std::max(max_hid, M * (size_t)(C * h->cfg.mlp_hidden_mult));
         max_rows = std::max(max_rows, Mw);
@@ -528,7 +553,7 @@ static WindowGeom geom(int H, int W, int shift) {
 // writes the resampled map to `out` (scale != 0) — for scale == 0 the result is left in xw.
 static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, int H) {
     const LayerW& lw = c.h->layers[li];
-    const int C = lw.C, ld = ldc(C), ldq = ldc(3 * C), ldh = C * c.h->cfg.mlp_hidden_mult;
+    const int C = lw.C, ld = ldc(C), ldq = 3 * lw.heads * lw.hdp, ldh = C * c.h->cfg.mlp_hidden_mult;
     const int B = c.B, W = c.W;
     const long long M = (long long)B * H * W;
     const float* src = x_in;
@@ -537,7 +562,7 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
         const long long nwin = (long long)B * g.nW, Mw = nwin * 16;
         const BlockW& bw = lw.blk[j];
         op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
-        op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, C, nwin, (j & 1) != 0, g);
+        op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, lw.hdp, C, nwin, (j & 1) != 0, g);
         op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
         op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
         op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);

@@ -13,6 +13,9 @@
 namespace escb {
 
 inline int ldc(int C) { return (C + 3) & ~3; }
+// head width of the qkv buffer [rows][3][heads][hdp]: heads are padded to a multiple of 4 floats (15 -> 16) so the
+// attention core reads q / k / v rows with aligned vector loads; 6 stays 6 (8-byte vectors)
+inline int head_pad(int hd) { return hd == 6 ? 6 : (hd + 3) & ~3; }
 
 struct LnW { const float* g; const float* b; };     // padded to a multiple of 4 with zeros
 
@@ -23,7 +26,7 @@ struct BlockW {
 };
 
 struct LayerW {
-    int C, heads, hd, depth, scale, out_dim;         // scale: 0 none, 1 down (PatchMerge), 2 up (PatchSplit)
+    int C, heads, hd, hdp, depth, scale, out_dim;    // scale: 0 none, 1 down (PatchMerge), 2 up (PatchSplit); hdp = head_pad(hd)
     BlockW blk[ESCB_MAX_DEPTH];
     LnW sn;
     GemmWeight sub;
@@ -98,7 +101,7 @@ constexpr int kEmbedMaxK = 16;     // 2 * patch_freq * patch_time <= 16
 // ---- swin.cu : one reference SwinBlock = qkv -> attention -> proj -> mlp1 -> mlp2
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq);
 void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
-                  int hd, int C, long long nwin, bool masked, const WindowGeom& g);
+                  int hd, int hdp, int C, long long nwin, bool masked, const WindowGeom& g);
 void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
              const WindowGeom& g, long long M);
 void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh);

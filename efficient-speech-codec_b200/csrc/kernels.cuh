@@ -9,16 +9,20 @@
 namespace escb {
 
 // ------------------------------------------------------------------------------------------------ attention core
-// One thread per (window, head, query token): 16 scores, softmax, 16-term weighted sum of V — all in registers.
-// q/k/v of the block's windows are staged in shared memory with coalesced float4 loads; the 16 lanes that share
-// a head read K/V rows as broadcasts.  Mirrors WindowAttention.forward (attention.py:222-241): q is scaled before
-// the product, the relative-position bias and then the 0/-100 shifted-window mask are added, softmax over keys.
-// qkv rows are window-major (row = window*16 + token), columns [3][heads][HD].
-template <int HD>
+// One thread per (window, head, query token): 16 scores, softmax, 16-term weighted sum of V, all in registers.
+// Mirrors WindowAttention.forward (attention.py:222-241): q is scaled before the product, the relative-position
+// bias and then the 0/-100 shifted-window mask are added, softmax over keys.
+// qkv rows are window-major (row = window*16 + token) with columns [3][heads][HDP] (head_pad: the qkv GEMM writes
+// heads padded to a multiple of 4 floats), so the block's windows are staged with one coalesced float4 copy and
+// every q / k / v row is read from shared memory with aligned vector loads (the 16 lanes of a head read K / V rows
+// as broadcasts).  The outputs go back through shared memory and leave as one coalesced float4 copy.
+template <int HD, int HDP>
 __global__ void window_attn_kernel(const float* __restrict__ qkv, const int ldq, float* __restrict__ out,
                                    const int ldo, const float* __restrict__ relbias, const int nH, const int C,
                                    const long long nwin_total, const int wpb, const float scale, const int masked,
                                    const int nW, const int nWw, const int Hp, const int Wp) {
+    constexpr int VW = (HDP % 4 == 0) ? 4 : 2;              // vector width of the shared-memory row reads
+    constexpr int NV = HDP / VW;
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     const long long win0 = (long long)blockIdx.x * wpb;
@@ -32,61 +36,98 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const int ldq,
     __syncthreads();
     const int per_win = 16 * nH;
     const int lw = tid / per_win;
-    if (lw >= nwin) return;
     const int r = tid - lw * per_win;
     const int h = r >> 4, i = r & 15;
-    const float* base = sm + (long long)lw * 16 * ldq;
+    const bool active = lw < nwin;
+    float o[HDP];
+    if (active) {
+        const float* base = sm + (long long)lw * 16 * ldq;
+        auto ldrow = [&](const float* p, float (&v)[HDP]) {
+#pragma unroll
+            for (int u = 0; u < NV; ++u) {
+                if (VW == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(p + 4 * u);
+                    v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+                } else {
+                    const float2 t = *reinterpret_cast<const float2*>(p + 2 * u);
+                    v[2 * u] = t.x; v[2 * u + 1] = t.y;
+                }
+            }
+        };
+        float q[HDP];
+        ldrow(base + i * ldq + h * HDP, q);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) q[d] *= scale;
 
-    float q[HD];
+        float s[16];
+        const float* kb = base + nH * HDP + h * HDP;
+        const float4* bias = reinterpret_cast<const float4*>(relbias + (h * 16 + i) * 16);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = base[i * ldq + h * HD + d] * scale;
-
-    float s[16];
-    const float* kb = base + C + h * HD;
-    const float* bias = relbias + (h * 16 + i) * 16;
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bv = __ldg(bias + j4);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        float acc = 0.f;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                float kr[HDP];
+                ldrow(kb + j * ldq, kr);
+                float acc = 0.f;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) acc = fmaf(q[d], kb[j * ldq + d], acc);
-        s[j] = acc + __ldg(bias + j);
-    }
-    if (masked) {
-        // region ids of the shifted map (attention.py:56-75): 0 | 1 | 2 along each axis, id = 3*rh + rw
-        const int win = (int)((win0 + lw) % nW);
-        const int wh = win / nWw, ww = win - wh * nWw;
-        int rh[4], rw[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int hs = wh * 4 + a, ws = ww * 4 + a;
-            rh[a] = hs < Hp - 4 ? 0 : (hs < Hp - 2 ? 1 : 2);
-            rw[a] = ws < Wp - 4 ? 0 : (ws < Wp - 2 ? 1 : 2);
+                for (int d = 0; d < HD; ++d) acc = fmaf(q[d], kr[d], acc);
+                s[j] = acc + bb[jj];
+            }
         }
-        const int mine = 3 * rh[i >> 2] + rw[i & 3];
+        if (masked) {
+            // region ids of the shifted map (attention.py:56-75): 0 | 1 | 2 along each axis, id = 3*rh + rw
+            const int win = (int)((win0 + lw) % nW);
+            const int wh = win / nWw, ww = win - wh * nWw;
+            int rh[4], rw[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (3 * rh[j >> 2] + rw[j & 3] != mine) s[j] += -100.0f;
+            for (int a = 0; a < 4; ++a) {
+                const int hs = wh * 4 + a, ws = ww * 4 + a;
+                rh[a] = hs < Hp - 4 ? 0 : (hs < Hp - 2 ? 1 : 2);
+                rw[a] = ws < Wp - 4 ? 0 : (ws < Wp - 2 ? 1 : 2);
+            }
+            const int mine = 3 * rh[i >> 2] + rw[i & 3];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (3 * rh[j >> 2] + rw[j & 3] != mine) s[j] += -100.0f;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) mx = fmaxf(mx, s[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = 0.f;
+        const float* vb = base + 2 * nH * HDP + h * HDP;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float p = s[j] * inv;
+            float vr[HDP];
+            ldrow(vb + j * ldq, vr);
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o[d] = fmaf(p, vr[d], o[d]);
+        }
     }
-    float mx = s[0];
+    __syncthreads();                                       // every q / k / v read is done: reuse the tile for the outputs
+    const int pitch = ldo + 4;
+    if (active) {
+        float* op = sm + (lw * 16 + i) * pitch + h * HD;
 #pragma unroll
-    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, s[j]);
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-    const float inv = 1.0f / sum;
-    float o[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    const float* vb = base + 2 * C + h * HD;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float p = s[j] * inv;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = fmaf(p, vb[j * ldq + d], o[d]);
+        for (int d = 0; d < HD; ++d) op[d] = o[d];
     }
-    float* op = out + ((win0 + lw) * 16 + i) * (long long)ldo + h * HD;
-#pragma unroll
-    for (int d = 0; d < HD; ++d) op[d] = o[d];
+    __syncthreads();
+    {
+        const int l4 = ldo / 4, n4 = nwin * 16 * l4;
+        float4* dst = reinterpret_cast<float4*>(out + win0 * 16 * (long long)ldo);
+        for (int e = tid; e < n4; e += blockDim.x) {
+            const int row = e / l4, c4 = e - row * l4;
+            dst[e] = *reinterpret_cast<const float4*>(sm + row * pitch + c4 * 4);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ RVQ argmin

@@ -1,5 +1,7 @@
 // Swin block ops: host launchers over gemm.cuh / kernels.cuh.  Reference: attention.py:129-178 (SwinBlock),
 // :215-244 (WindowAttention), :258-272 (FeedForward); scale.py:83-145 (PatchMerge / PatchSplit).
+#include <algorithm>
+
 #include "internal.h"
 #include "kernels.cuh"
 
@@ -9,7 +11,7 @@ static inline LnParams lnp(Launcher& L, const LnW& w) { return LnParams{w.g, w.b
 static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
 
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq) {
-    L.begin(OP_QKV, 2.0 * M * w.qkv.N * w.qkv.K, 4.0 * (1.0 * M * w.qkv.K + 1.0 * M * w.qkv.N));
+    L.begin(OP_QKV, 2.0 * M * 3.0 * w.qkv.K * w.qkv.K, 4.0 * (1.0 * M * w.qkv.K + 3.0 * M * w.qkv.K));   // true dims (3C x C)
     AWindow al{x, ld, g};
     EpiRows<false, false> ep{qkv, w.qkv.bias, nullptr, ldq, 0};
     if (L.tc) ++L.launches, L.note(tc::launch<true, AWindow, EpiRows<false, false>>(L.st, al, lnp(L, w.n1), w.qkv, M, ep));
@@ -60,7 +62,7 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-template <int HD>
+template <int HD, int HDP>
 static cudaError_t launch_attn(cudaStream_t st, const float* qkv, int ldq, float* att, int ldo, const float* relbias,
                                int heads, int C, long long nwin, bool masked, const WindowGeom& g) {
     int wpb = 256 / (16 * heads);
@@ -68,22 +70,22 @@ static cudaError_t launch_attn(cudaStream_t st, const float* qkv, int ldq, float
     while ((wpb * 16 * heads) % 32) ++wpb;
     const int threads = wpb * 16 * heads;
     if (threads > 1024) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)wpb * 16 * ldq * sizeof(float);
+    const size_t smem = (size_t)wpb * 16 * std::max(ldq, ldo + 4) * sizeof(float);
     const float scale = (float)(1.0 / sqrt((double)HD));
     const long long blocks = (nwin + wpb - 1) / wpb;
-    window_attn_kernel<HD><<<(unsigned)blocks, threads, smem, st>>>(qkv, ldq, att, ldo, relbias, heads, C, nwin, wpb,
-                                                                   scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp);
+    window_attn_kernel<HD, HDP><<<(unsigned)blocks, threads, smem, st>>>(qkv, ldq, att, ldo, relbias, heads, C, nwin, wpb,
+                                                                        scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp);
     return cudaGetLastError();
 }
 
 #define ESCB_ATTN_HDS(X) X(4) X(6) X(8) X(12) X(15) X(16) X(24) X(32)
 
 void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
-                  int hd, int C, long long nwin, bool masked, const WindowGeom& g) {
+                  int hd, int hdp, int C, long long nwin, bool masked, const WindowGeom& g) {
     L.begin(OP_ATTN, 1024.0 * nwin * C, 4.0 * 16.0 * nwin * 4.0 * C);
     cudaError_t e = cudaErrorInvalidValue;
-    switch (hd) {
-#define X(n) case n: e = launch_attn<n>(L.st, qkv, ldq, att, ldo, relbias, heads, C, nwin, masked, g); break;
+    if (hdp == head_pad(hd)) switch (hd) {
+#define X(n) case n: e = launch_attn<n, (n == 6 ? 6 : (n + 3) & ~3)>(L.st, qkv, ldq, att, ldo, relbias, heads, C, nwin, masked, g); break;
         ESCB_ATTN_HDS(X)
 #undef X
         default: break;
@@ -102,7 +104,7 @@ bool attention_supported(int hd) {
 
 cudaError_t swin_init() {
     cudaError_t e = cudaSuccess;
-#define X(n) if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+#define X(n) if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attn_kernel<n, (n == 6 ? 6 : (n + 3) & ~3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     ESCB_ATTN_HDS(X)
 #undef X
     return e;
