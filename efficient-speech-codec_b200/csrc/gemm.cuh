@@ -252,10 +252,15 @@ struct GemmLauncher {
         const int list[] = {TNS...};
         int best = list[0];
         long long best_pad = -1;
+        // least column padding; on a tie the wider tile, unless the grid would leave SMs idle (skinny problems
+        // such as the product-VQ down-projection: 43 row tiles), where the narrower tile doubles the CTAs
+        const long long ntm64 = (M + 63) / 64;
         for (int c : list) {
             const int bn = 16 * c;
             const long long pad = (long long)((w.N + bn - 1) / bn) * bn;
-            if (best_pad < 0 || pad < best_pad || (pad == best_pad && c > best)) { best = c; best_pad = pad; }
+            const int wider = c > best ? c : best;
+            const bool small_grid = ntm64 * ((w.N + 16 * wider - 1) / (16 * wider)) < 148;
+            if (best_pad < 0 || pad < best_pad || (pad == best_pad && (small_grid ? c < best : c > best))) { best = c; best_pad = pad; }
         }
         cudaError_t err = cudaErrorInvalidValue;
         const bool hit = ((best == TNS ? (err = go<TNS>(st, al, ln, w, M, ep), true) : false) || ...);

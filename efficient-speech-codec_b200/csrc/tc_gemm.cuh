@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 
@@ -168,7 +169,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 template <bool LN, class AL, class EP, int E>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
-               const int NB, const int resident) {
+               const int NB, const int resident, const int pf_dist) {
     static_assert(sizeof(typename EP::Row) <= 16, "epilogue row context must fit 16 bytes");
     using R = Roles<E>;
     constexpr int EPI_WARPS = R::EPI_WARPS, PROD_WARPS = R::PROD_WARPS, PROD_THREADS = R::PROD_THREADS;
@@ -234,8 +235,8 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 eok[lane] = ok;
                 __syncwarp();
             }
-            if (part == 0 && tile + (int)gridDim.x < ntiles) {   // residual rows of the next tile -> L2
-                const long long mn = (long long)((tile + gridDim.x) / ntn) * BM + q * 32 + lane;
+            if (part == 0 && pf_dist > 0 && tile + pf_dist * (int)gridDim.x < ntiles) {   // residual rows of a later tile -> L2
+                const long long mn = (long long)((tile + pf_dist * gridDim.x) / ntn) * BM + q * 32 + lane;
                 typename EP::Row pr;
                 if (mn < M && ep.row(mn, pr)) ep.prefetch(pr, N);
             }
@@ -313,8 +314,8 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     al.init((long long)cur_m0 + r0 + ROW_STEP * i, M, myrow[i]);
                     if (al.valid(myrow[i])) cur_vm |= 1u << i;
                 }
-                const int next = ld_tile + gridDim.x;
-                if (next < ntiles && pt < 512) {           // pull the following tile's rows into L2 (four threads per row)
+                const int next = ld_tile + pf_dist * gridDim.x;
+                if (pf_dist > 0 && next < ntiles && pt < 512) {           // pull the following tile's rows into L2 (four threads per row)
                     typename AL::Row pr;
                     if (PROD_THREADS >= 512) {
                         al.init((long long)(next / ntn) * BM + (pt >> 2), M, pr);
@@ -544,7 +545,7 @@ inline Tiling choose_tiling(int N, int K, int wide) {
     for (int ntn = 1; ntn <= 64; ++ntn)
         for (int nsub = 1; nsub <= MAX_REG; ++nsub) {
             const int bn = (((N + ntn * nsub - 1) / (ntn * nsub)) + 15) / 16 * 16;
-            if (bn > (nsub == 1 ? MAX_BN : 128) || bn * nsub > TMEM_COLS) continue;
+            if (bn > (nsub == 1 ? MAX_BN : 144) || bn * nsub > TMEM_COLS) continue;
             if (bn < 48 && ntn * nsub > 1) continue;
             const long long stage = (long long)bn * 256;
             const bool res = stage * nkb * nsub <= B_BUDGET && nkb * nsub <= MAX_NB;
@@ -587,7 +588,9 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
     long long grid = sm_count();
     if (w.resident) grid = grid / w.ntn * w.ntn;       // a resident CTA serves one n-tile
     if (grid > ntiles) grid = ntiles;
-    tc_gemm_kernel<LN, AL, EP, E><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident);
+    static int pf_dist = -1;            // tiles of L2 prefetch distance (ESCB_TC_PREFETCH, default 1)
+    if (pf_dist < 0) { const char* e = getenv("ESCB_TC_PREFETCH"); pf_dist = e ? atoi(e) : 1; }
+    tc_gemm_kernel<LN, AL, EP, E><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
     return cudaGetLastError();
 }
 
