@@ -1,5 +1,7 @@
 // Swin block ops: host launchers over gemm.cuh / kernels.cuh.  Reference: attention.py:129-178 (SwinBlock),
 // :215-244 (WindowAttention), :258-272 (FeedForward); scale.py:83-145 (PatchMerge / PatchSplit).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "internal.h"
@@ -65,7 +67,9 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
 template <int HD, int HDP>
 static cudaError_t launch_attn(cudaStream_t st, const float* qkv, int ldq, float* att, int ldo, const float* relbias,
                                int heads, int C, long long nwin, bool masked, const WindowGeom& g) {
-    int wpb = 256 / (16 * heads);
+    static int target = -1;            // threads per block to aim for (ESCB_ATTN_THREADS, default 128: more, smaller blocks overlap their load and compute phases)
+    if (target < 0) { const char* e = getenv("ESCB_ATTN_THREADS"); target = e ? atoi(e) : 128; }
+    int wpb = target / (16 * heads);
     if (wpb < 1) wpb = 1;
     while ((wpb * 16 * heads) % 32) ++wpb;
     const int threads = wpb * 16 * heads;

@@ -545,7 +545,7 @@ inline Tiling choose_tiling(int N, int K, int wide) {
     for (int ntn = 1; ntn <= 64; ++ntn)
         for (int nsub = 1; nsub <= MAX_REG; ++nsub) {
             const int bn = (((N + ntn * nsub - 1) / (ntn * nsub)) + 15) / 16 * 16;
-            if (bn > (nsub == 1 ? MAX_BN : 144) || bn * nsub > TMEM_COLS) continue;
+            if (bn > MAX_BN || bn * nsub > TMEM_COLS) continue;
             if (bn < 48 && ntn * nsub > 1) continue;
             const long long stage = (long long)bn * 256;
             const bool res = stage * nkb * nsub <= B_BUDGET && nkb * nsub <= MAX_NB;
@@ -553,7 +553,9 @@ inline Tiling choose_tiling(int N, int K, int wide) {
             if (!res && nb < 2) continue;
             const double padn = (double)bn * nsub * ntn;
             const int nreg = TMEM_COLS / bn < MAX_REG ? TMEM_COLS / bn : MAX_REG;
-            const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + (!res && nb < 3 ? 0.2 : 0.0) + (nreg <= nsub ? 0.15 : 0.0)) +
+            // an SS-mode MMA reads (128 + bn) * 32 bytes of shared memory per bn / 2 clocks: wider is cheaper per MAC
+            const double narrow = ntn * nsub > 1 ? (bn < 96 ? 0.3 : (bn < 128 ? 0.15 : (bn < 176 ? 0.05 : 0.0))) : 0.0;
+            const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + (nreg <= nsub ? 0.15 : 0.0) + narrow) +
                                 96.0 * ntn + 4.0 * nsub;
             if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0}; }
         }
