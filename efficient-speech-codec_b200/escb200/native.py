@@ -158,9 +158,10 @@ class Handle:
         check(self._lib.escb_create(C.byref(make_config(spec)), C.byref(self._h)))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) and self._h.value:
-            self._lib.escb_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._h = None                     # before the call: close() also runs as __del__ at interpreter shutdown
+            self._lib.escb_destroy(h)
 
     __del__ = close
 
