@@ -211,13 +211,14 @@ struct Packer {
         put_matrix(gw, W.host.data(), (int)W.shape[0], (int)W.shape[1], bname ? &w(bname) : nullptr, wide);
     }
     // W [N][K] row-major (nn.Linear layout), optional bias [N]
-    void put_matrix(GemmWeight& gw, const float* W, int N, int K, const std::vector<float>* bias, int wide = 0) {
+    void put_matrix(GemmWeight& gw, const float* W, int N, int K, const std::vector<float>* bias, int wide = 0,
+                    const tc::Tiling* forced = nullptr) {
         std::vector<float> t;
         init_gemm(gw, N, K, t);
         for (int n = 0; n < N; ++n)
             for (int k = 0; k < K; ++k) t[(size_t)k * gw.ldw + n] = W[(size_t)n * K + k];
         put(&gw.wt, t);
-        put_tc(gw, t, wide);
+        put_tc(gw, t, wide, forced);
         gw.bias = nullptr;
         if (bias) put(&gw.bias, *bias);
     }
@@ -237,6 +238,30 @@ struct Packer {
                 }
         put_matrix(gw, Wp.data(), Np, C, &Bp);
     }
+    // the same projection for the fused attention epilogue (tc_gemm.cuh): columns [head slot][q | k | v][hdp] in
+    // sub-tiles of 144 = whole heads, zero rows / bias in the padding slots.  Returns false when the head width
+    // does not divide the sub-tile (the layer then keeps the unfused qkv + window_attn_kernel pair).
+    bool put_qkv_heads(GemmWeight& gw, const std::string& wname, const std::string& bname, int C, int heads) {
+        const int hd = C / heads, hdp = head_pad(hd);
+        gw = GemmWeight{};
+        if (kAttnBN % (3 * hdp) != 0 || !attention_fusable(hd)) return false;
+        const int hpb = kAttnBN / (3 * hdp);
+        int nsubs = 0;
+        const tc::Tiling tl = tc::attn_tiling((heads + hpb - 1) / hpb, C, &nsubs);
+        const std::vector<float>& W = w(wname);
+        const std::vector<float>& B = w(bname);
+        const int Np = nsubs * kAttnBN;
+        std::vector<float> Wp((size_t)Np * C, 0.f), Bp((size_t)Np, 0.f);
+        for (int hh = 0; hh < heads; ++hh)
+            for (int part = 0; part < 3; ++part)
+                for (int d = 0; d < hd; ++d) {
+                    const int n = part * C + hh * hd + d, np = (hh * 3 + part) * hdp + d;
+                    memcpy(&Wp[(size_t)np * C], &W[(size_t)n * C], (size_t)C * sizeof(float));
+                    Bp[np] = B[n];
+                }
+        put_matrix(gw, Wp.data(), Np, C, &Bp, 0, &tl);
+        return true;
+    }
     static float tf32_rna(float x) {           // cvt.rna.tf32.f32: nearest, ties away, 10 mantissa bits kept
         uint32_t u;
         memcpy(&u, &x, 4);
@@ -246,11 +271,11 @@ struct Packer {
         return x;
     }
     // tcgen05 operand images from the packed Wt [Kpad][ldw] (see TcWeight in gemm.cuh)
-    void put_tc(GemmWeight& gw, const std::vector<float>& t, int wide = 0) {
+    void put_tc(GemmWeight& gw, const std::vector<float>& t, int wide = 0, const tc::Tiling* forced = nullptr) {
         TcWeight& w = gw.tc;
         w.N = gw.N;
         w.K = gw.K;
-        const tc::Tiling tl = tc::choose_tiling(gw.N, gw.K, wide);
+        const tc::Tiling tl = forced ? *forced : tc::choose_tiling(gw.N, gw.K, wide);
         w.wide = wide;
         w.ntn = tl.ntn;
         w.nsub = tl.nsub;
@@ -309,6 +334,7 @@ static void pack_layer(Packer& P, int li) {
         P.put_ln(bw.n1, b + ".norm1", d.C);
         P.put_ln(bw.n2, b + ".norm2", d.C);
         P.put_qkv(bw.qkv, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
+        P.put_qkv_heads(bw.qkvh, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
         P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str());
         P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str(), 1);
         P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str());
@@ -549,6 +575,13 @@ static WindowGeom geom(int H, int W, int shift) {
     return g;
 }
 
+// widest layer whose qkv GEMM runs the attention core in its epilogue (ESCB_FUSE_ATTN_MAXC, 0 = never)
+static int fuse_attn_max_c() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ESCB_FUSE_ATTN_MAXC"); v = e ? atoi(e) : 1 << 20; }
+    return v;
+}
+
 // TransformerLayer.forward (attention.py:48-91).  Reads x_in (never written), runs the blocks in `xw`, then
 // writes the resampled map to `out` (scale != 0) — for scale == 0 the result is left in xw.
 static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, int H) {
@@ -561,8 +594,12 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
         const WindowGeom g = geom(H, W, (j & 1) ? 2 : 0);
         const long long nwin = (long long)B * g.nW, Mw = nwin * 16;
         const BlockW& bw = lw.blk[j];
-        op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
-        op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, lw.hdp, C, nwin, (j & 1) != 0, g);
+        if (c.L.tc && bw.qkvh.tc.img && C <= fuse_attn_max_c())
+            op_qkv_attn(c.L, bw, lw.heads, lw.hd, src, ld, g, Mw, c.wk.att, ld, (j & 1) != 0);
+        else {
+            op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
+            op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, lw.hdp, C, nwin, (j & 1) != 0, g);
+        }
         op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
         op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
         op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);
@@ -1079,7 +1116,7 @@ int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, i
 static const char* const kOpNames[OP_COUNT] = {
     "stft_gemm", "patch_embed", "qkv_gemm", "window_attention", "proj_gemm", "mlp1_gemm", "mlp2_gemm", "merge_gemm",
     "split_gemm", "pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "vq_loss", "deembed_conv5x5_gemm",
-    "deembed_conv3x3", "istft_gemm", "layout"};
+    "deembed_conv3x3", "istft_gemm", "layout", "qkv_attention_fused"};
 
 int escb_profile_begin(escb_handle* h) {
     if (!h) return fail(ESCB_EINVAL, "null handle");

@@ -22,6 +22,7 @@ struct LnW { const float* g; const float* b; };     // padded to a multiple of 4
 struct BlockW {
     LnW n1, n2;
     GemmWeight qkv, proj, fc1, fc2;
+    GemmWeight qkvh;                                 // qkv in head-major columns for the fused attention epilogue (tc.img null: not fusable)
     const float* relbias;                            // [heads][16][16], gathered from the (49, heads) table
 };
 
@@ -58,7 +59,7 @@ struct FrontW {
 // Kernel classes for launch accounting / per-op timing (escb_profile_begin/end).
 enum OpId {
     OP_STFT, OP_EMBED, OP_QKV, OP_ATTN, OP_PROJ, OP_MLP1, OP_MLP2, OP_MERGE, OP_SPLIT, OP_PVQ_DOWN, OP_ARGMIN,
-    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_COUNT
+    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_QKV_ATTN, OP_COUNT
 };
 static_assert(OP_COUNT == ESCB_NUM_OPS, "escb200.h ESCB_NUM_OPS out of date");
 
@@ -102,6 +103,9 @@ constexpr int kEmbedMaxK = 16;     // 2 * patch_freq * patch_time <= 16
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq);
 void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
                   int hd, int hdp, int C, long long nwin, bool masked, const WindowGeom& g);
+void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x, int ld, const WindowGeom& g, long long M,
+                 float* att, int ldo, bool masked);
+bool attention_fusable(int hd);
 void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
              const WindowGeom& g, long long M);
 void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh);

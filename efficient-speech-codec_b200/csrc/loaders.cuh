@@ -334,6 +334,26 @@ struct EpiWindow {
     }
 };
 
+// Fused window-attention epilogue of the tcgen05 engine (tc_gemm.cuh): the qkv accumulator never leaves the SM.
+// Column layout of the GEMM is [head slot][q | k | v][HDP] in sub-tiles of kAttnBN columns = HPB whole heads; the
+// engine's epilogue warps compute softmax(q k^T * scale + relbias + mask) v per (window, head) and write
+// out[row][h*HD + d] (rows in window order, like window_attn_kernel).  WindowAttention.forward attention.py:222-241.
+constexpr int kAttnBN = 144;
+template <int HD_, int HDP_>
+struct EpiAttn {
+    static constexpr bool kAttn = true;
+    static constexpr int HD = HD_, HDP = HDP_, HPB = kAttnBN / (3 * HDP_);
+    static_assert(HPB * 3 * HDP_ == kAttnBN, "head width must divide the sub-tile");
+    float* out;
+    int ldo;
+    const float* bias;      // [slots][3][HDP], zero in the padding
+    const float* relbias;   // [heads][16][16]
+    int heads;
+    float scale;
+    int masked, nW, nWw, Hp, Wp;
+    struct Row { int unused; };
+};
+
 // PatchSplit pixel shuffle (scale.py:16-23,142-144): row m = (b,h,w); n < Co goes to freq row 2h, the rest to 2h+1.
 struct EpiSplit {
     float* Y;

@@ -20,6 +20,39 @@ void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGe
     else L.note(GemmLauncher<true, AWindow, EpiRows<false, false>, 7, 9>::launch(L.st, al, lnp(L, w.n1), w.qkv, M, ep));
 }
 
+// qkv projection + window attention core in one launch: LN1 -> window gather -> GEMM -> attention in the epilogue
+#define ESCB_FUSED_HDS(X) X(6) X(8) X(12) X(15) X(16) X(24)
+bool attention_fusable(int hd) {
+    switch (hd) {
+#define X(n) case n: return true;
+        ESCB_FUSED_HDS(X)
+#undef X
+        default: return false;
+    }
+}
+
+void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x, int ld, const WindowGeom& g, long long M,
+                 float* att, int ldo, bool masked) {
+    const int C = w.qkvh.K;
+    L.begin(OP_QKV_ATTN, 2.0 * M * 3.0 * C * C + 64.0 * M * C, 4.0 * 2.0 * M * C);    // qkv + (q k^T, p v) ; x in, attention out
+    const float scale = (float)(1.0 / sqrt((double)hd));
+    cudaError_t e = cudaErrorInvalidValue;
+    AWindow al{x, ld, g};
+    switch (hd) {
+#define X(n)                                                                                                        \
+    case n: {                                                                                                       \
+        using EP = EpiAttn<n, (n == 6 ? 6 : (n + 3) & ~3)>;                                                         \
+        EP ep{att, ldo, w.qkvh.bias, w.relbias, heads, scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp};             \
+        e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                                   \
+    } break;
+        ESCB_FUSED_HDS(X)
+#undef X
+        default: break;
+    }
+    ++L.launches;          // the LayerNorm statistics pre-kernel
+    L.note(e);
+}
+
 void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
              const WindowGeom& g, long long M) {
     L.begin(OP_PROJ, 2.0 * M * w.proj.N * w.proj.K, 4.0 * 3.0 * M * w.proj.K);

@@ -27,7 +27,7 @@ EXPORTS = [
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
 ]
-ESCB_NUM_OPS = 17
+ESCB_NUM_OPS = 18
 
 
 class NativeLibraryMissing(ImportError):
