@@ -291,7 +291,7 @@ struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
         return RES ? *reinterpret_cast<const float4*>(R + c.r + n) : zero4();
     }
     __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4 r) const {
-        if (GELU) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (GELU) { gelu_erf2(v.x, v.y); gelu_erf2(v.z, v.w); }   // (scalar tails in store() use erff: same function to ~1e-7)
         if (RES) { v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w; }
         *reinterpret_cast<float4*>(Y + c.y + n) = v;
     }

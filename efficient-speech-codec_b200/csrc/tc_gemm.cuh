@@ -53,7 +53,7 @@ constexpr int NBARS = 2 * MAX_NA + 2 * MAX_NB + 2 * MAX_REG;
 // Role split: E epilogue warps per TMEM lane quadrant.  E = 2: 8 epilogue + 16 producer warps, 3 A slots (the
 // default); E = 4: 16 epilogue + 8 producer warps, 2 A slots, for the GELU GEMM (small K, wide N) whose erf
 // epilogue would otherwise stall the tensor pipe.
-template <int E>
+template <int E, bool ATTN = false>
 struct Roles {
     static constexpr int EPI_WARPS = 4 * E;
     static constexpr int PROD_WARPS = 24 - EPI_WARPS;
@@ -62,15 +62,17 @@ struct Roles {
     static constexpr int ROW_STEP = 4 * PROD_WARPS;        // distance between a thread's rows
     static constexpr int DEPTH = 8 / RPT;                  // producer jobs with loads in flight
     static constexpr int NA = E == 4 ? 2 : 3;              // A ring slots
-    // per-warp staging: a 32 x 16 transpose tile; the 8-warp split also hosts the fused attention epilogue, whose
-    // K / V image [HD][32] and output tile [32][HD | 1] need up to 896 floats (HD = 24)
-    static constexpr int STG_WARP_BYTES = E == 2 ? 3584 : 2048;
+    // per-warp staging: a 32 x 16 transpose tile; the fused attention epilogue keeps a K / V image [HD][32] and an
+    // output tile [32][HD + 4] there, up to 896 floats (HD = 24)
+    static constexpr int STG_WARP_BYTES = ATTN ? 3584 : 2048;
     static constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
     static constexpr int CTX_BYTES = EPI_WARPS * 32 * 16;
     static constexpr int TAIL_BYTES = STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4 + NBARS * 8 + 16;
     static constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
 };
+constexpr int kAttnE = 4;             // role split of the fused attention kernel: 16 epilogue warps
 inline int b_budget(int wide) { return wide ? Roles<4>::B_BUDGET : Roles<2>::B_BUDGET; }
+inline int b_budget_attn() { return Roles<kAttnE, true>::B_BUDGET; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -189,20 +191,6 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
     for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]) :: "memory");
 }
 
-// packed fp32 pairs: Blackwell's FFMA2 does two independent fp32 FMAs (same rounding as the scalar one) per issue slot
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
 template <int N>
 __device__ __forceinline__ void add_bias(float* v, const float* __restrict__ b) {     // b 8-byte aligned, N even
     if constexpr (N % 4 == 0) {
@@ -258,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
                const int NB, const int resident, const int pf_dist) {
     static_assert(sizeof(typename EP::Row) <= 16, "epilogue row context must fit 16 bytes");
-    using R = Roles<E>;
+    using R = Roles<E, IsAttn<EP>::value>;
     constexpr int EPI_WARPS = R::EPI_WARPS, PROD_WARPS = R::PROD_WARPS, PROD_THREADS = R::PROD_THREADS;
     constexpr int RPT = R::RPT, ROW_STEP = R::ROW_STEP, DEPTH = R::DEPTH, NA = R::NA;
     constexpr int STG_BYTES = R::STG_BYTES, CTX_BYTES = R::CTX_BYTES;
@@ -350,7 +338,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 const int h0 = ((tile % ntn) * nsub + sub) * HPB;
                 // heads of the sub-tile alternate between the quadrant's E warps; with an odd head count the warp
                 // that takes the extra head alternates from tile to tile
-                for (int hl = (HPB & 1) ? (part + tile_it) % E : part; hl < HPB; hl += E) {
+                for (int hl = (HPB % E) ? (part + tile_it) % E : part; hl < HPB; hl += E) {
                     const int h = h0 + hl;
                     if (h >= ep.heads) break;               // zero-padded head slots of the last sub-tile
                     const float* bh = ep.bias + h * (3 * HDP);
@@ -825,7 +813,7 @@ inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const int ntn = (nsubs_total + max_sub - 1) / max_sub;
     const int nsub = (nsubs_total + ntn - 1) / ntn;
     const long long stage = 144LL * 256;
-    const bool res = stage * nkb * nsub <= b_budget(0) && nkb * nsub <= MAX_NB;
+    const bool res = stage * nkb * nsub <= b_budget_attn() && nkb * nsub <= MAX_NB;
     if (ntn_out_subs) *ntn_out_subs = ntn * nsub;
     return Tiling{144, nsub, ntn, nkb, res ? 1 : 0};
 }
@@ -842,7 +830,7 @@ inline int sm_count() {
 
 template <bool LN, class AL, class EP, int E>
 inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, const TcWeight& w, long long M, const EP& ep) {
-    using R = Roles<E>;
+    using R = Roles<E, IsAttn<EP>::value>;
     static bool configured = false;     // per instantiation
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
@@ -870,13 +858,14 @@ inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, con
     const TcWeight& w = gw.tc;
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
     if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
-    if ((w.wide != 0) != WIDE) return cudaErrorInvalidValue;
+    constexpr int E = IsAttn<EP>::value ? kAttnE : (WIDE ? 4 : 2);
+    if ((w.wide != 0) != (E == 4)) return cudaErrorInvalidValue;
     if (LN) {
         if (!ln.stats) return cudaErrorInvalidValue;
         const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
         if (e != cudaSuccess) return e;
     }
-    return launch_e<LN, AL, EP, WIDE ? 4 : 2>(st, al, ln, w, M, ep);
+    return launch_e<LN, AL, EP, E>(st, al, ln, w, M, ep);
 }
 
 }  // namespace tc
