@@ -106,6 +106,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a converged warp.  Issuing tcgen05.mma / cp.async.bulk under `if (elect_one())` lets ptxas emit them as
+// plain uniform-datapath instructions; under `if (lane == 0)` each one is wrapped in an ELECT / BRA.U.ANY loop
+// (5 extra dependent instructions per MMA, which made the single issuing thread the bound of every N <= 192 GEMM).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -653,7 +666,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     const uint32_t bs = resident ? (uint32_t)(kb * nsub + sub) : bslot;
                     { TC_T0(t_); mbar_wait(b_full + 8 * bs, resident ? 0u : bphase); TC_ACC(2, t_); }
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint64_t b_hi = make_desc(sB + bs * b_stage), b_lo = make_desc(sB + bs * b_stage + b_img);
                         const uint32_t d_sub = tmem + reg * BN;
                         for (int ks = 0; ks < ksteps; ++ks) {
@@ -676,7 +689,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         }
     } else {
         // ======================================================================================== weight loader
-        if (lane == 0) {
+        if (elect_one()) {
             const uint8_t* wimg = (const uint8_t*)w.img;
             if (resident) {
                 if ((int)blockIdx.x < ntiles) {
