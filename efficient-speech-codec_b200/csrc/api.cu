@@ -572,6 +572,7 @@ static WindowGeom geom(int H, int W, int shift) {
     WindowGeom g;
     g.H = H; g.W = W; g.Hp = round_up(H, 4); g.Wp = round_up(W, 4); g.shift = shift;
     g.nWw = g.Wp / 4; g.nW = (g.Hp / 4) * g.nWw;
+    g.dW = FastDiv::make((unsigned)g.nW); g.dWw = FastDiv::make((unsigned)g.nWw);
     return g;
 }
 

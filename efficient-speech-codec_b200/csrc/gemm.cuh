@@ -28,7 +28,17 @@ struct LnParams {
     unsigned long long* trace;   // ESCB_TC_TRACE builds: 16 counters of this launch (null otherwise)
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 16-byte load: activations are read once per GEMM, so they bypass L1 allocation (ESCB_LDG_PLAIN: plain __ldg)
+__device__ __forceinline__ float4 ldg4(const float* p) {
+#ifdef ESCB_LDG_PLAIN
+    return __ldg(reinterpret_cast<const float4*>(p));
+#else
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#endif
+}
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 mask4(float4 v, int k, int K) {
     if (k + 1 >= K) v.y = 0.f;

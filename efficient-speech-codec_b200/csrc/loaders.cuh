@@ -29,15 +29,35 @@ struct ARows {
 // (attention.py:137-153, 246-250).  Row m = ((b*nWh + wh)*nWw + ww)*16 + (i*4 + j) reads the token at
 // h = (4*wh + i + shift) % Hp, w = (4*ww + j + shift) % Wp; tokens in the padding are all-zero rows
 // (the reference pads AFTER norm1, so they bypass LayerNorm).
+// Division by a launch-invariant divisor as multiply-high + shift: exact for every n < 2^31 with
+// magic = ceil(2^(31 + s) / d), s = ceil(log2 d) (d = 1 is flagged by magic = 0).  The window index arithmetic below
+// runs once per row per tile in the A producers and epilogues, where a hardware-emulated 32-bit division (~25
+// instructions) was a third of the producers' time.
+struct FastDiv {
+    unsigned d, magic, shift;
+    __host__ __device__ static FastDiv make(unsigned d) {
+        FastDiv f{d, 0u, 0u};
+        if (d > 1) {
+            unsigned s = 0;
+            while ((1ull << s) < d) ++s;
+            f.magic = (unsigned)(((1ull << (31 + s)) + d - 1) / d);
+            f.shift = s - 1;
+        }
+        return f;
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return magic ? __umulhi(n, magic) >> shift : n; }
+};
+
 struct WindowGeom {
     int H, W, Hp, Wp, shift, nWw, nW;   // nW = (Hp/4)*(Wp/4)
+    FastDiv dW, dWw;                    // by nW, by nWw
     __device__ __forceinline__ long long token(long long m) const {   // m < 2^31 (checked by the launchers)
         const unsigned mm = (unsigned)m;
         const int t = (int)(mm & 15u);
         const unsigned wi = mm >> 4;
-        const unsigned b = wi / (unsigned)nW;
+        const unsigned b = dW.div(wi);
         const unsigned win = wi - b * (unsigned)nW;
-        const int wh = (int)(win / (unsigned)nWw), ww = (int)(win - (unsigned)wh * (unsigned)nWw);
+        const int wh = (int)dWw.div(win), ww = (int)(win - (unsigned)wh * (unsigned)nWw);
         int h = wh * 4 + (t >> 2) + shift, w = ww * 4 + (t & 3) + shift;
         if (h >= Hp) h -= Hp;
         if (w >= Wp) w -= Wp;
@@ -351,6 +371,7 @@ struct EpiAttn {
     int heads;
     float scale;
     int masked, nW, nWw, Hp, Wp;
+    FastDiv dW, dWw;
     struct Row { int unused; };
 };
 

@@ -42,7 +42,7 @@ void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x
 #define X(n)                                                                                                        \
     case n: {                                                                                                       \
         using EP = EpiAttn<n, (n == 6 ? 6 : (n + 3) & ~3)>;                                                         \
-        EP ep{att, ldo, w.qkvh.bias, w.relbias, heads, scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp};             \
+        EP ep{att, ldo, w.qkvh.bias, w.relbias, heads, scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp, g.dW, g.dWw};             \
         e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                                   \
     } break;
         ESCB_FUSED_HDS(X)

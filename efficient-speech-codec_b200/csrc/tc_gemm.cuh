@@ -330,8 +330,9 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             unsigned diff = 0;                             // keys of my window that lie in another shift region than me
             if (ep.masked) {
                 // region ids of the shifted map (attention.py:56-75): 0 | 1 | 2 along each axis, id = 3*rh + rw
-                const int win = (int)((unsigned)(m >> 4) % (unsigned)ep.nW);
-                const int wh = win / ep.nWw, ww = win - wh * ep.nWw;
+                const unsigned wi = (unsigned)(m >> 4);
+                const int win = (int)(wi - ep.dW.div(wi) * (unsigned)ep.nW);
+                const int wh = (int)ep.dWw.div((unsigned)win), ww = win - wh * ep.nWw;
                 int rh[4], rw[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
@@ -666,6 +667,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     const uint32_t bs = resident ? (uint32_t)(kb * nsub + sub) : bslot;
                     { TC_T0(t_); mbar_wait(b_full + 8 * bs, resident ? 0u : bphase); TC_ACC(2, t_); }
                     tc_fence_after();
+                    TC_T0(ti_);
                     if (elect_one()) {
                         const uint64_t b_hi = make_desc(sB + bs * b_stage), b_lo = make_desc(sB + bs * b_stage + b_img);
                         const uint32_t d_sub = tmem + reg * BN;
@@ -680,6 +682,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                         if (sub + 1 == nsub) umma_commit(a_empty + 8 * aslot);
                     }
                     __syncwarp();
+                    TC_ACC(3, ti_);
                     if (!resident && ++bslot == (uint32_t)NB) { bslot = 0; bphase ^= 1; }
                     if (++reg == (uint32_t)nreg) { reg = 0; rphase ^= 1; }
                 }
@@ -723,7 +726,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         unsigned long long* t = ln.trace;
         if (warp == EPI_BASE) { atomicAdd(t + 1, (unsigned long long)tr[0]); atomicAdd(t + 9, (unsigned long long)total); atomicAdd(t + 13, 1ull); }
         if (warp == PROD_BASE) { atomicAdd(t + 2, (unsigned long long)tr[0]); atomicAdd(t + 3, (unsigned long long)tr[1]); atomicAdd(t + 4, (unsigned long long)tr[2]); atomicAdd(t + 10, (unsigned long long)total); atomicAdd(t + 12, (unsigned long long)tr[3]); }
-        if (warp == EPI_WARPS + PROD_WARPS) { atomicAdd(t + 5, (unsigned long long)tr[0]); atomicAdd(t + 6, (unsigned long long)tr[1]); atomicAdd(t + 7, (unsigned long long)tr[2]); atomicAdd(t + 11, (unsigned long long)total); }
+        if (warp == EPI_WARPS + PROD_WARPS) { atomicAdd(t + 5, (unsigned long long)tr[0]); atomicAdd(t + 6, (unsigned long long)tr[1]); atomicAdd(t + 7, (unsigned long long)tr[2]); atomicAdd(t + 0, (unsigned long long)tr[3]); atomicAdd(t + 11, (unsigned long long)total); }
         if (warp == EPI_WARPS + PROD_WARPS + 1) { atomicAdd(t + 8, (unsigned long long)tr[0]); }
         if (tid == 0 && blockIdx.x == 0) { t[14] = (unsigned long long)ntiles; t[15] = ((unsigned long long)w.N << 40) | ((unsigned long long)w.K << 20) | ((unsigned long long)w.BN << 8) | ((unsigned long long)w.nsub << 4) | (unsigned long long)w.resident; }
     }

@@ -41,7 +41,7 @@ for phase in ("encode", "decode"):
     L.escb_debug_trace(hp, buf.ctypes.data_as(C.c_void_p))
     t = buf.reshape(1024, 16).astype(np.float64)
     print(f"== {phase}: per launch: N K BN nsub res | tiles ctas | kclk/cta | epi wait% | prod: wait_a_empty% convert% issue% | "
-          f"mma: wait_a_full% wait_acc_empty% wait_b_full% | prod tile-init%")
+          f"mma: wait_a_full% wait_acc_empty% wait_b_full% issue% | prod tile-init%")
     for i in range(1024):
         n = t[i, 13]
         if n == 0:
@@ -51,7 +51,7 @@ for phase in ("encode", "decode"):
         tot = t[i, 9] / n
         pe = 100 * t[i, 1] / max(t[i, 9], 1)
         pw, pc, pi = (100 * t[i, k] / max(t[i, 10], 1) for k in (2, 3, 4))
-        ma, mc, mb = (100 * t[i, k] / max(t[i, 11], 1) for k in (5, 6, 7))
+        ma, mc, mb, mi = (100 * t[i, k] / max(t[i, 11], 1) for k in (5, 6, 7, 0))
         lw = 100 * t[i, 12] / max(t[i, 10], 1)   # producer: per-tile init + prefetch share
         print(f"{i:3d} N={N:4d} K={K:4d} BN={BN:3d}x{nsub} r{res} | {int(t[i,14]):5d} {int(n):3d} | {tot/1e3:7.1f} | {pe:4.0f} | "
-              f"{pw:4.0f} {pc - pw:4.0f} {pi:4.0f} | {ma:4.0f} {mc:4.0f} {mb:4.0f} | {lw:4.0f}")
+              f"{pw:4.0f} {pc - pw:4.0f} {pi:4.0f} | {ma:4.0f} {mc:4.0f} {mb:4.0f} {mi:4.0f} | {lw:4.0f}")
