@@ -68,6 +68,7 @@ struct escb_handle {
     std::atomic<long long> launches{0};
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
+    int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     unsigned long long* trace = nullptr;   // ESCB_TC_TRACE builds only
     // grow-only scratch for the *_host entry points
@@ -390,6 +391,26 @@ static void pack_quant(Packer& P, int q) {
     P.put(&qw.down.wt, down);
     P.put(&qw.up.wt, up);
     P.put_tc(qw.up, up);
+    // per-group down-projections: group g owns kref in [start_g, start_g + vq_g), i.e. (with equal thirds that are
+    // multiples of Hq) the (o, c) range [g*run, (g+1)*run) of every h run; its K index is kg = h*run + (o*C + c - g*run)
+    qw.run = 0;
+    if ((2 * C) % 3 == 0 && ((2 * C / 3) % 2) == 0 && vq[0] == vq[1] && vq[1] == vq[2] && vq[0] == (2 * C / 3) * Hq) {
+        const int run = 2 * C / 3;
+        qw.run = run;
+        for (int g = 0; g < 3; ++g) {
+            std::vector<float> dg;
+            Packer::init_gemm(qw.down_g[g], dd, run * Hq, dg);
+            const std::vector<float>& dw = P.w(p + ".down_projs." + std::to_string(g) + ".weight");   // [d][vq_g]
+            for (int hh = 0; hh < Hq; ++hh)
+                for (int oc = g * run; oc < (g + 1) * run; ++oc) {
+                    const int o = oc / C, c = oc - o * C;
+                    const int kl = o * (C * Hq) + c * Hq + hh - start[g];
+                    const int kg = hh * run + (oc - g * run);
+                    for (int j = 0; j < dd; ++j) dg[(size_t)kg * qw.down_g[g].ldw + j] = dw[(size_t)j * vq[g] + kl];
+                }
+            P.put(&qw.down_g[g].wt, dg);
+        }
+    }
     // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
     std::vector<float> raw((size_t)3 * K * dd), cbt((size_t)3 * K * dd), cn((size_t)3 * K);
     for (int g = 0; g < 3; ++g) {
@@ -576,13 +597,6 @@ static WindowGeom geom(int H, int W, int shift) {
     return g;
 }
 
-// widest layer whose qkv GEMM runs the attention core in its epilogue (ESCB_FUSE_ATTN_MAXC, 0 = never)
-static int fuse_attn_max_c() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("ESCB_FUSE_ATTN_MAXC"); v = e ? atoi(e) : 1 << 20; }
-    return v;
-}
-
 // TransformerLayer.forward (attention.py:48-91).  Reads x_in (never written), runs the blocks in `xw`, then
 // writes the resampled map to `out` (scale != 0) — for scale == 0 the result is left in xw.
 static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, int H) {
@@ -595,7 +609,7 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
         const WindowGeom g = geom(H, W, (j & 1) ? 2 : 0);
         const long long nwin = (long long)B * g.nW, Mw = nwin * 16;
         const BlockW& bw = lw.blk[j];
-        if (c.L.tc && bw.qkvh.tc.img && C <= fuse_attn_max_c())
+        if (c.L.tc && bw.qkvh.tc.img && C <= c.h->fuse_attn_max_c)
             op_qkv_attn(c.L, bw, lw.heads, lw.hd, src, ld, g, Mw, c.wk.att, ld, (j & 1) != 0);
         else {
             op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
@@ -782,6 +796,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     h->cfg = c;
     if (const char* e = getenv("ESCB_GEMM")) h->use_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
+    if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
     h->F = c.in_freq; h->n_fft = n_fft; h->win = c.win_length; h->hop = c.hop_length;

@@ -101,9 +101,9 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <int TM, int TN, bool LN, class AL, class EP>
-__global__ void __launch_bounds__(kGemmThreads)
-gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const int ldw, const long long M,
-            const int N, const int K, const int Kpad, const int ntn, const EP ep) {
+__device__ __forceinline__ void gemm_tile(const AL& al, const LnParams& ln, const float* __restrict__ Wt, const int ldw,
+                                          const long long M, const int N, const int K, const int Kpad, const int ntn,
+                                          const EP& ep) {
     constexpr int BM = 16 * TM, BN = 16 * TN;
     constexpr int AP = BM + 4;
     constexpr int PA = BM / 64;                         // float4 A loads per thread per k-tile
@@ -249,6 +249,27 @@ gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const 
     }
 }
 
+template <int TM, int TN, bool LN, class AL, class EP>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_kernel(const AL al, const LnParams ln, const float* __restrict__ Wt, const int ldw, const long long M,
+            const int N, const int K, const int Kpad, const int ntn, const EP ep) {
+    gemm_tile<TM, TN, LN, AL, EP>(al, ln, Wt, ldw, M, N, K, Kpad, ntn, ep);
+}
+
+// Three independent GEMMs of one shape in one grid (blockIdx.y picks the problem): the product-VQ down-projection
+// is block diagonal over its 3 groups, so each group multiplies only its own third of the frame - a third of the
+// flops of the stacked weight and three times the CTAs for a 43-row-tile problem.
+template <class AL, class EP>
+struct Gemm3 { AL al[3]; EP ep[3]; const float* wt[3]; };
+template <int TM, int TN, class AL, class EP>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm3_kernel(const __grid_constant__ Gemm3<AL, EP> g, const int ldw, const long long M, const int N, const int K,
+             const int Kpad, const int ntn) {
+    const LnParams ln{nullptr, nullptr, 0.f, nullptr, nullptr};
+    const int y = blockIdx.y;
+    gemm_tile<TM, TN, false, AL, EP>(g.al[y], ln, g.wt[y], ldw, M, N, K, Kpad, ntn, g.ep[y]);
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 // Operand images for the tcgen05 engine (tc_gemm.cuh): per (n tile, 32-wide K block) one contiguous chunk
 // [hi image | lo image], each BN rows x 128 bytes in the 128-byte-swizzled K-major layout, hi = tf32(w),
@@ -324,5 +345,16 @@ struct GemmLauncher {
         return err;
     }
 };
+
+template <int TN, class AL, class EP>
+inline cudaError_t launch_gemm3(cudaStream_t st, const Gemm3<AL, EP>& g, const GemmWeight& w, long long M) {
+    const int ntn = (w.N + 16 * TN - 1) / (16 * TN);
+    if (M <= 0) return cudaSuccess;
+    if (3 * ((M + 127) / 128) * ntn >= 2 * 148)
+        gemm3_kernel<8, TN, AL, EP><<<dim3((unsigned)(((M + 127) / 128) * ntn), 3), kGemmThreads, 0, st>>>(g, w.ldw, M, w.N, w.K, w.Kpad, ntn);
+    else
+        gemm3_kernel<4, TN, AL, EP><<<dim3((unsigned)(((M + 63) / 64) * ntn), 3), kGemmThreads, 0, st>>>(g, w.ldw, M, w.N, w.K, w.Kpad, ntn);
+    return cudaGetLastError();
+}
 
 }  // namespace escb

@@ -36,6 +36,8 @@ struct LayerW {
 struct QuantW {
     int in_dim, in_freq, d, frame_dim, ncodes;
     GemmWeight down;                                 // K = frame_dim in (h,o,c) order, N = 3d (block structured)
+    GemmWeight down_g[3];                            // per group: K = frame_dim / 3 (its (o,c) third of every h run), N = d
+    int run;                                         // 2C/3 when the groups are equal (o,c) thirds (else 0: stacked path only)
     GemmWeight up;                                   // K = 3d, N = frame_dim in (h,o,c) order
     const float* raw;                                // [3][ncodes][d]
     const float* cbt;                                // [3][d][ncodes] L2-normalised, transposed

@@ -6,6 +6,25 @@
 
 namespace escb {
 
+// Division by a launch-invariant divisor as multiply-high + shift: exact for every n < 2^31 with
+// magic = ceil(2^(31 + s) / d), s = ceil(log2 d) (d = 1 is flagged by magic = 0).  The window index arithmetic below
+// runs once per row per tile in the A producers and epilogues, where a hardware-emulated 32-bit division (~25
+// instructions) was a third of the producers' time.
+struct FastDiv {
+    unsigned d, magic, shift;
+    __host__ __device__ static FastDiv make(unsigned d) {
+        FastDiv f{d, 0u, 0u};
+        if (d > 1) {
+            unsigned s = 0;
+            while ((1ull << s) < d) ++s;
+            f.magic = (unsigned)(((1ull << (31 + s)) + d - 1) / d);
+            f.shift = s - 1;
+        }
+        return f;
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return magic ? __umulhi(n, magic) >> shift : n; }
+};
+
 // =============================================================================================== A loaders
 // Contract: init(m, M, row) fills the per-row context; valid(row) == false means the whole row is zero
 // (out-of-range row or a zero-padded token); load1(row,k) returns element k (< K); load4(row,k,K) returns
@@ -29,25 +48,6 @@ struct ARows {
 // (attention.py:137-153, 246-250).  Row m = ((b*nWh + wh)*nWw + ww)*16 + (i*4 + j) reads the token at
 // h = (4*wh + i + shift) % Hp, w = (4*ww + j + shift) % Wp; tokens in the padding are all-zero rows
 // (the reference pads AFTER norm1, so they bypass LayerNorm).
-// Division by a launch-invariant divisor as multiply-high + shift: exact for every n < 2^31 with
-// magic = ceil(2^(31 + s) / d), s = ceil(log2 d) (d = 1 is flagged by magic = 0).  The window index arithmetic below
-// runs once per row per tile in the A producers and epilogues, where a hardware-emulated 32-bit division (~25
-// instructions) was a third of the producers' time.
-struct FastDiv {
-    unsigned d, magic, shift;
-    __host__ __device__ static FastDiv make(unsigned d) {
-        FastDiv f{d, 0u, 0u};
-        if (d > 1) {
-            unsigned s = 0;
-            while ((1ull << s) < d) ++s;
-            f.magic = (unsigned)(((1ull << (31 + s)) + d - 1) / d);
-            f.shift = s - 1;
-        }
-        return f;
-    }
-    __device__ __forceinline__ unsigned div(unsigned n) const { return magic ? __umulhi(n, magic) >> shift : n; }
-};
-
 struct WindowGeom {
     int H, W, Hp, Wp, shift, nWw, nW;   // nW = (Hp/4)*(Wp/4)
     FastDiv dW, dWw;                    // by nW, by nWw
@@ -148,6 +148,57 @@ struct AFrame {
             e.x -= d.x; e.y -= d.y; e.z -= d.z; e.w -= d.w;
         }
         return e;
+    }
+    __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
+};
+
+// One group's third of that frame: in the (h, o, c) order a group is the (o, c) sub-range [goff, goff + run) of each
+// of the Hq runs (run = 2C/3), so row m, element k reads x[b, h*W + 2t, goff + k - h*run] with h = k / run.
+struct AFrameG {
+    const float* E;
+    const float* D;     // may be null
+    int Hq, W, C, run, goff, vec4;      // vec4: run and goff are multiples of 4 (one aligned 16-byte load per call)
+    FastDiv drun;
+    struct Row { long long base; };
+    __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
+        r.base = -1;
+        if (m < M) {
+            const unsigned T = (unsigned)W >> 1, mm = (unsigned)m;
+            const unsigned b = mm / T, t = mm - b * T;
+            r.base = ((long long)b * Hq * (long long)W + 2 * t) * C + goff;
+        }
+    }
+    __device__ __forceinline__ bool valid(const Row& r) const { return r.base >= 0; }
+    __device__ __forceinline__ long long off(const Row& r, int k) const {
+        const int h = (int)drun.div((unsigned)k);
+        return r.base + (long long)h * W * C + (k - h * run);
+    }
+    __device__ __forceinline__ float load1(const Row& r, int k) const {
+        const long long o = off(r, k);
+        return D ? __ldg(E + o) - __ldg(D + o) : __ldg(E + o);
+    }
+    __device__ __forceinline__ float2 load2(const Row& r, int k) const {     // k even: never straddles a run
+        const long long o = off(r, k);
+        float2 e = __ldg(reinterpret_cast<const float2*>(E + o));
+        if (D) {
+            const float2 d = __ldg(reinterpret_cast<const float2*>(D + o));
+            e.x -= d.x; e.y -= d.y;
+        }
+        return e;
+    }
+    __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const {
+        if (vec4) {
+            const long long o = off(r, k);
+            float4 e = ldg4(E + o);
+            if (D) {
+                const float4 d = ldg4(D + o);
+                e.x -= d.x; e.y -= d.y; e.z -= d.z; e.w -= d.w;
+            }
+            return e;
+        }
+        const float2 a = load2(r, k);
+        const float2 b = (k + 2 < K) ? load2(r, k + 2) : make_float2(0.f, 0.f);
+        return make_float4(a.x, a.y, b.x, b.y);
     }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };

@@ -13,6 +13,19 @@ void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* de
     const long long M = (long long)B * (W / 2);
     L.begin(OP_PVQ_DOWN, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim + 3.0 * q.d));
     // stays on the fp32 SIMT engine: its output feeds the argmin directly (and is no faster on the tensor cores)
+    if (q.run > 0 && q.d <= 48) {
+        // block-diagonal form: three GEMMs [M, frame/3] x [frame/3, d] in one grid (gemm.cuh Gemm3)
+        Gemm3<AFrameG, EpiRows<false, false>> g;
+        for (int i = 0; i < 3; ++i) {
+            const int goff = i * q.run;
+            g.al[i] = AFrameG{enc, dec, q.in_freq, W, q.in_dim, q.run, goff, (q.run % 4 == 0 && q.in_dim % 4 == 0) ? 1 : 0,
+                              FastDiv::make((unsigned)q.run)};
+            g.ep[i] = EpiRows<false, false>{ze + i * q.d, nullptr, nullptr, ldz, 0};
+            g.wt[i] = q.down_g[i].wt;
+        }
+        L.note(launch_gemm3<3>(L.st, g, q.down_g[0], M));
+        return;
+    }
     L.note(GemmLauncher<false, AFrame, EpiRows<false, false>, 3, 6>::launch(L.st, al, noln(L), q.down, M, ep));
 }
 

@@ -230,6 +230,24 @@ def test_full_batch_properties(base0):
     assert maxabs(o.decode(co, fs)[0], audio[35].cpu()) <= AUDIO_TOL
 
 
+@pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"}])
+def test_engine_variants_agree(base0, env, monkeypatch):
+    """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair and the fp32 SIMT engine are
+    three implementations of the same layers: identical code indices, audio equal to fp32 reassociation noise
+    (ragged width: padded windows + shift masks on every level)."""
+    x = synth_audio(3, 16000 + 80 * 4 * 7, seed=41).cuda()
+    codes0, fs0 = base0.encode(x, 6)
+    audio0 = base0.decode(codes0, fs0)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                     # read by escb_create: per handle
+    other = make_native(BASE, 0)[0]
+    codes1, fs1 = other.encode(x, 6)
+    audio1 = other.decode(codes1, fs1)
+    assert fs0 == fs1
+    assert torch.equal(codes0, codes1)
+    assert maxabs(audio0.cpu(), audio1.cpu()) <= 2e-5
+
+
 def test_host_buffer_path_equals_device_path(base0):
     """escb_encode_host / escb_decode_host (CPU tensors in, CPU tensors out) give the same bits."""
     x = synth_audio(3, 16000, seed=31)
