@@ -28,7 +28,10 @@ struct FastDiv {
 // =============================================================================================== A loaders
 // Contract: init(m, M, row) fills the per-row context; valid(row) == false means the whole row is zero
 // (out-of-range row or a zero-padded token); load1(row,k) returns element k (< K); load4(row,k,K) returns
-// elements k..k+3 with those >= K zeroed (k % 4 == 0, k < K).
+// elements k..k+3 with those >= K zeroed (k % 4 == 0, k < K).  load4_raw(row,k,K) is the same load WITHOUT any
+// instruction that consumes the loaded registers (kRawMask == true: the caller zeroes the elements >= K itself, later):
+// the tcgen05 producers issue it several K blocks ahead, and a select on the loaded value would park the warp on the
+// load right at the issue point (it did: mask4 inside load4 cost the producers half their time).
 
 // Dense rows X[m*ld + k].
 struct ARows {
@@ -41,6 +44,8 @@ struct ARows {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+    static constexpr bool kRawMask = true;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int) const { return ldg4(r.p + k); }
     __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const { prefetch_row(r.p, K, part); }
 };
 
@@ -81,6 +86,8 @@ struct AWindow {
     __device__ __forceinline__ bool valid(const Row& r) const { return r.p != nullptr; }
     __device__ __forceinline__ float load1(const Row& r, int k) const { return __ldg(r.p + k); }
     __device__ __forceinline__ float4 load4(const Row& r, int k, int K) const { return mask4(ldg4(r.p + k), k, K); }
+    static constexpr bool kRawMask = true;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int) const { return ldg4(r.p + k); }
     __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const { prefetch_row(r.p, K, part); }
 };
 
@@ -110,6 +117,8 @@ struct AMerge {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row& r, int K, int part) const {
         for (int k = (part >> 1) * 32; k < C; k += 64) prefetch_l2(((part & 1) ? r.p1 : r.p0) + k);
     }
@@ -149,6 +158,8 @@ struct AFrame {
         }
         return e;
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
@@ -200,6 +211,8 @@ struct AFrameG {
         const float2 b = (k + 2 < K) ? load2(r, k + 2) : make_float2(0.f, 0.f);
         return make_float4(a.x, a.y, b.x, b.y);
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
@@ -233,6 +246,8 @@ struct ACodes {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
@@ -264,6 +279,8 @@ struct AIm2col {
         if (hh < 0 || hh >= H || ww < 0 || ww >= W) return zero4();
         return mask4(ldg4(r.p + ((long long)dh * W + dw) * ld + c), c, C);
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
@@ -297,6 +314,8 @@ struct AStftFrames {
         v.w = (k + 3 < K) ? load1(r, k + 3) : 0.f;
         return v;
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 
@@ -325,6 +344,8 @@ struct AIstft {
         const int t = r.j - dt;
         return (t >= 0 && t < T) ? ldg4(r.p + (long long)t * F2 + cf) : zero4();
     }
+    static constexpr bool kRawMask = false;
+    __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
     __device__ __forceinline__ void prefetch(const Row&, int, int) const {}
 };
 

@@ -593,7 +593,9 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             j.m0 = cur_m0;
 #pragma unroll
             for (int i = 0; i < RPT; ++i)
-                j.a[i] = (((cur_vm >> i) & 1u) && k < K) ? al.load4(myrow[i], k, K) : zero4();
+                // plain GEMMs issue the raw load and mask at conversion time; the LayerNorm GEMMs measured slower that
+                // way (their rows were just read by ln_stats_kernel and arrive from L2 almost at once), so they keep load4
+                j.a[i] = (((cur_vm >> i) & 1u) && k < K) ? (LN ? al.load4(myrow[i], k, K) : al.load4_raw(myrow[i], k, K)) : zero4();
             if (++ld_kb == nkb) { ld_kb = 0; ld_tile += gridDim.x; }
             return true;
         };
@@ -618,6 +620,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             for (int i = 0; i < RPT; ++i) {
                 const int r = r0 + ROW_STEP * i;
                 float4 v = j.a[i];
+                if (AL::kRawMask && !LN) v = mask4(v, k, K);      // (the LN branch masks after normalising)
                 if (LN && k < K && ((j.vm >> i) & 1u)) {
                     const float mean = st[i].x, rstd = st[i].y;
                     v.x = (v.x - mean) * rstd * g.x + be.x;
