@@ -66,7 +66,7 @@ void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, 
     L.begin(OP_MLP1, 2.0 * M * w.fc1.N * w.fc1.K, 4.0 * M * (w.fc1.K + w.fc1.N));
     ARows al{x, ld};
     EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
-    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, true>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, kMlp1Wide != 0>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
 }
 
