@@ -269,7 +269,16 @@ def main_b200(args):
         roof = {"bound": "tensor", "achieved": tflops, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tflops / peaks["tensor"]}
     else:
         roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
-    roof.update({"traffic": None, "kernel": top, "launches": tv["launches"], "avg_launch_ms": tv["ms"] / max(tv["launches"], 1),
+    traffic, traffic_src = None, None
+    try:                                     # measured DRAM bytes per launch of that class (tools/ncu_traffic.py over one step)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.config == "base" and B == 36 and top in tj["classes"]:
+            traffic = tj["classes"][top]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's launches of this class)"
+    except (OSError, ValueError, KeyError):
+        pass
+    roof.update({"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": tv["bytes"] / max(tv["launches"], 1),
+                 "kernel": top, "launches": tv["launches"], "avg_launch_ms": tv["ms"] / max(tv["launches"], 1),
                  "share_of_step": tv["ms"] / tot_ms, "flop_per_byte": ai, "achieved_tflops": tflops, "achieved_gbs": gbs,
                  "peak_source": peaks["src"] + " (MEASURED_PEAKS.json bf16 sustained / hbm copy)",
                  "whole_step_tflops": value / N * GFLOP_PER_CLIP[args.config] / 1e3,

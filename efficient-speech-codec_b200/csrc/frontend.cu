@@ -31,7 +31,8 @@ void op_patch_embed(Launcher& L, const FrontW& f, const float* Sf, int B, int T,
 }
 
 void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, int H, int W, float* Y1, float* Xf) {
-    L.begin(OP_DEEMBED1, 2.0 * B * H * W * f.de1.N * 25 * f.C0, 4.0 * B * H * W * (f.C0 + f.de1.N));
+    const double n1 = (double)f.C0 * f.pf * f.pt;          // true output channels (the packed weight pads them to the pixel pitch)
+    L.begin(OP_DEEMBED1, 2.0 * B * H * W * n1 * 25 * f.C0, 4.0 * B * H * W * (f.C0 + n1));
     AIm2col al{tok, ld, H, W, f.C0};
     EpiDeembed ep{Y1, f.de1.bias, ld, H, W, f.C0, f.pf, f.pt};
     if (L.tc) L.note(tc::launch<false, AIm2col, EpiDeembed>(L.st, al, noln(L), f.de1, (long long)B * H * W, ep));

@@ -507,11 +507,11 @@ struct EpiFrame {
     __device__ __forceinline__ void prefetch(const Row&, int) const {}
 };
 
-// conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78):
-// n = (s1*pt + s2)*C + c -> pixel (pf*h + s1, pt*w + s2), channel c.
+// conv5x5 bias + pixel shuffle (3,2) to channels-last [B, pf*H, pt*W, ldy] (scale.py:77-78).  The GEMM's columns are
+// padded to the pixel pitch: n = (s1*pt + s2)*ldy + c -> pixel (pf*h + s1, pt*w + s2), channel c (c >= C: zero pad).
 struct EpiDeembed {
     float* Y;
-    const float* bias;
+    const float* bias;      // [pf*pt*ldy], zero in the pad channels
     int ldy, H, W, C, pf, pt;
     struct Row { long long y; };
     __device__ __forceinline__ bool row(long long m, Row& c) const {
@@ -519,19 +519,19 @@ struct EpiDeembed {
         c.y = (((long long)bh * pf) * (long long)(W * pt) + (long long)w * pt) * ldy;
         return true;
     }
-    __device__ __forceinline__ void put(const Row& c, int n, float v) const {
-        const int s = n / C, ch = n - s * C;
+    __device__ __forceinline__ long long at(const Row& c, int n) const {
+        const int s = n / ldy, ch = n - s * ldy;
         const int s1 = s / pt, s2 = s - s1 * pt;
-        Y[c.y + ((long long)s1 * (W * pt) + s2) * ldy + ch] = v;
+        return c.y + ((long long)s1 * (W * pt) + s2) * ldy + ch;
     }
-    __device__ __forceinline__ void store(const Row& c, int n, float v) const { put(c, n, v + __ldg(bias + n)); }
-    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {
-        store(c, n, v.x); store(c, n + 1, v.y); store(c, n + 2, v.z); store(c, n + 3, v.w);
+    __device__ __forceinline__ void store(const Row& c, int n, float v) const { Y[at(c, n)] = v + __ldg(bias + n); }
+    __device__ __forceinline__ void store4(const Row& c, int n, float4 v) const {   // n % 4 == 0: one pixel, aligned
+        const float4 b = ldg4(bias + n);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        *reinterpret_cast<float4*>(Y + at(c, n)) = v;
     }
     __device__ __forceinline__ float4 bias4(int n) const { return ldg4(bias + n); }
-    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const {
-        put(c, n, v.x); put(c, n + 1, v.y); put(c, n + 2, v.z); put(c, n + 3, v.w);
-    }
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { *reinterpret_cast<float4*>(Y + at(c, n)) = v; }
     __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
     __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4_nb(c, n, v); }
     __device__ __forceinline__ void prefetch(const Row&, int) const {}
