@@ -277,7 +277,8 @@ struct AIm2col {
         const int dh = tap / 5 - 2, dw = tap % 5 - 2;
         const int hh = r.h + dh, ww = r.w + dw;
         if (hh < 0 || hh >= H || ww < 0 || ww >= W) return zero4();
-        return mask4(ldg4(r.p + ((long long)dh * W + dw) * ld + c), c, C);
+        // every token row is read by 25 taps of ~25 neighbouring rows: let L1 keep it (ldg4 is the no-allocate stream load)
+        return mask4(__ldg(reinterpret_cast<const float4*>(r.p + ((long long)dh * W + dw) * ld + c)), c, C);
     }
     static constexpr bool kRawMask = false;
     __device__ __forceinline__ float4 load4_raw(const Row& r, int k, int K) const { return load4(r, k, K); }
@@ -531,7 +532,8 @@ struct EpiDeembed {
         *reinterpret_cast<float4*>(Y + at(c, n)) = v;
     }
     __device__ __forceinline__ float4 bias4(int n) const { return ldg4(bias + n); }
-    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { *reinterpret_cast<float4*>(Y + at(c, n)) = v; }
+    // streaming store: the 800 MB pixel map must not push the 133 MB token map (re-read 25 times) out of L2
+    __device__ __forceinline__ void store4_nb(const Row& c, int n, float4 v) const { __stcs(reinterpret_cast<float4*>(Y + at(c, n)), v); }
     __device__ __forceinline__ float4 resid4(const Row&, int) const { return zero4(); }
     __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4) const { store4_nb(c, n, v); }
     __device__ __forceinline__ void prefetch(const Row&, int) const {}
