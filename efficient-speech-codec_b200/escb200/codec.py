@@ -151,6 +151,15 @@ class ESC(nn.Module):
             self._pinned[name] = buf
         return buf[:n].view(*shape)
 
+    def _host_in(self, name: str, t: torch.Tensor, dtype) -> torch.Tensor:
+        """A host tensor the DMA engine can read: ``t`` itself when it is already pinned, contiguous and of the right
+        dtype, else a copy in a cached pinned staging buffer."""
+        if t.dtype == dtype and t.is_contiguous() and t.is_pinned():
+            return t
+        buf = self._pin(name, tuple(t.shape), dtype)
+        buf.copy_(t)
+        return buf
+
     @staticmethod
     def _stream(dev: torch.device) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -183,12 +192,10 @@ class ESC(nn.Module):
                 native.check(lib.escb_encode(h.ptr, native.ptr(xx), B, Ls, num_streams, native.ptr(codes),
                                              native.ptr(ws), ws.numel(), self._stream(dev)))
             else:
-                xin = self._pin("audio_in", (B, Ls), torch.float32)
-                xin.copy_(x)
-                out = self._pin("codes_out", shape, torch.int64)
-                native.check(lib.escb_encode_host(h.ptr, native.ptr(xin), B, Ls, num_streams, native.ptr(out),
+                xin = self._host_in("audio_in", x, torch.float32)
+                codes = torch.empty(shape, dtype=torch.int64, pin_memory=True)    # caching host allocator: no clone
+                native.check(lib.escb_encode_host(h.ptr, native.ptr(xin), B, Ls, num_streams, native.ptr(codes),
                                                   self._stream(dev)))
-                codes = out.clone()
         return codes, (self.spec.bottom_freq, W)
 
     @torch.no_grad()
@@ -212,11 +219,9 @@ class ESC(nn.Module):
                 native.check(lib.escb_decode(h.ptr, native.ptr(cc), B, S, W, native.ptr(audio), None, native.ptr(ws),
                                              ws.numel(), self._stream(dev)))
             else:
-                cin = self._pin("codes_in", tuple(codes.shape), torch.int64)
-                cin.copy_(codes)
-                out = self._pin("audio_out", (B, n_out), torch.float32)
-                native.check(lib.escb_decode_host(h.ptr, native.ptr(cin), B, S, W, native.ptr(out), self._stream(dev)))
-                audio = out.clone()
+                cin = self._host_in("codes_in", codes, torch.int64)
+                audio = torch.empty((B, n_out), dtype=torch.float32, pin_memory=True)
+                native.check(lib.escb_decode_host(h.ptr, native.ptr(cin), B, S, W, native.ptr(audio), self._stream(dev)))
         return audio
 
     def forward_one_step(self, x, x_feat=None, num_streams=6, freeze_codebook=False):
