@@ -865,8 +865,11 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
     long long grid = sm_count();
     if (w.resident) grid = grid / w.ntn * w.ntn;       // a resident CTA serves one n-tile
     if (grid > ntiles) grid = ntiles;
-    static int pf_dist = -1;            // tiles of L2 prefetch distance (ESCB_TC_PREFETCH, default 1)
-    if (pf_dist < 0) { const char* e = getenv("ESCB_TC_PREFETCH"); pf_dist = e ? atoi(e) : 1; }
+    // tiles of L2 prefetch distance (ESCB_TC_PREFETCH overrides).  Measured per class at 36 clips: the fused attention
+    // kernel and the long-row GEMMs (K >= 2N: mlp2) are fastest without the prefetch, the others with one tile.
+    static int pf_env = -2;
+    if (pf_env == -2) { const char* e = getenv("ESCB_TC_PREFETCH"); pf_env = e ? atoi(e) : -1; }
+    const int pf_dist = pf_env >= 0 ? pf_env : ((IsAttn<EP>::value || w.K >= 2 * w.N) ? 0 : 1);
     tc_gemm_kernel<LN, AL, EP, E><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
     return cudaGetLastError();
 }
