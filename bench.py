@@ -42,6 +42,24 @@ GFLOP_PER_CLIP = {"base": 56.73, "large": 99.23}          # SURVEY.md section 8(
 METRIC = "clips_per_sec_3s_16khz_encode_decode"
 UNIT = "clips/s"
 
+# The contract is ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL prints its version banner there), so the real
+# stdout is kept aside for the result line and fd 1 is pointed at stderr for everything else.
+_RESULT = None
+
+
+def claim_stdout():
+    global _RESULT
+    if _RESULT is None:
+        sys.stdout.flush()
+        _RESULT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -142,7 +160,7 @@ def main_reference(args):
             "config": {"workload": f"ESC-{args.config} 9kbps encode+decode, 3 s synthetic clips, num_streams=6 (CPU sample)"},
             "cpu_baseline": dict(info, value=value, unit=UNIT),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -308,13 +326,14 @@ def main_b200(args):
                        "l2": "256 MiB buffer written between timed steps (outside the event pairs)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "rvq": rvq,
             "cpu_baseline": dict(cpu_info, value=cpu_v, unit=UNIT), "kernels": breakdown}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
