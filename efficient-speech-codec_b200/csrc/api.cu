@@ -390,7 +390,7 @@ static void pack_quant(Packer& P, int q) {
             }
     P.put(&qw.down.wt, down);
     P.put(&qw.up.wt, up);
-    P.put_tc(qw.up, up);
+    P.put_tc(qw.up, up, kPvqUpWide);
     // per-group down-projections: group g owns kref in [start_g, start_g + vq_g), i.e. (with equal thirds that are
     // multiples of Hq) the (o, c) range [g*run, (g+1)*run) of every h run; its K index is kg = h*run + (o*C + c - g*run)
     qw.run = 0;
