@@ -355,7 +355,7 @@ static void pack_layer(Packer& P, int li) {
         P.put_linear(lw.sub, d.prefix + ".subsample.down.weight", nullptr);
     } else if (d.scale == 2) {
         P.put_ln(lw.sn, d.prefix + ".subsample.norm", d.C);
-        P.put_linear(lw.sub, d.prefix + ".subsample.up.weight", nullptr);
+        P.put_linear(lw.sub, d.prefix + ".subsample.up.weight", nullptr, kSplitWide);
     }
 }
 

@@ -92,7 +92,7 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     EpiSplit ep{y, ldy, H, W, w.out_dim};
     const long long M = (long long)B * H * W;
     L.begin(OP_SPLIT, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
-    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide != 0>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 
