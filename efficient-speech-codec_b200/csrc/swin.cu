@@ -58,7 +58,7 @@ void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const floa
     L.begin(OP_PROJ, 2.0 * M * w.proj.N * w.proj.K, 4.0 * 3.0 * M * w.proj.K);
     ARows al{att, lda};
     EpiWindow ep{y, resid, w.proj.bias, ld, g};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow>(L.st, al, noln(L), w.proj, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow, kProjWide != 0>(L.st, al, noln(L), w.proj, M, ep));
     else L.note(GemmLauncher<false, ARows, EpiWindow, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.proj, M, ep));
 }
 
