@@ -338,7 +338,7 @@ static void pack_layer(Packer& P, int li) {
         P.put_qkv_heads(bw.qkvh, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
         P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str(), kProjWide);
         P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str(), kMlp1Wide);
-        P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str());
+        P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str(), kMlp2Wide);
         // relative-position bias gathered to [heads][16][16] (attention.py:190-205, 229-232)
         const std::vector<float>& table = P.w(b + ".attn.relative_position_bias_table");
         std::vector<float> rb((size_t)d.heads * 256);

@@ -74,7 +74,7 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
     L.begin(OP_MLP2, 2.0 * M * w.fc2.N * w.fc2.K, 4.0 * M * (w.fc2.K + 2.0 * w.fc2.N));
     ARows al{hid, ldh};
     EpiRows<false, true> ep{x, w.fc2.bias, x, ld, ld};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>>(L.st, al, noln(L), w.fc2, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>, kMlp2Wide != 0>(L.st, al, noln(L), w.fc2, M, ep));
     else L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.fc2, M, ep));
 }
 
