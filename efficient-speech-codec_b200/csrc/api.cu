@@ -68,6 +68,7 @@ struct escb_handle {
     std::atomic<long long> launches{0};
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
+    int ln_post = kLnPostDefault;   // ESCB_LN_POST bit mask (internal.h)
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     unsigned long long* trace = nullptr;   // ESCB_TC_TRACE builds only
@@ -223,6 +224,29 @@ struct Packer {
         gw.bias = nullptr;
         if (bias) put(&gw.bias, *bias);
     }
+    // Post-GEMM LayerNorm variant of a [N][K] weight whose input is LayerNorm(gamma, beta): the image holds
+    // W'[n][k] = gamma[k] W[n][k]; cs[n] = sum_k W'[n][k] and bw[n] = sum_k beta[k] W[n][k] (accumulated in double) feed
+    // the epilogue's rstd * (acc - mean * cs) + bw (tc_gemm.cuh LNP).
+    void put_ln_post(GemmWeight& gw, const float* W, int N, int K, const std::vector<float>* bias, const std::string& ln,
+                     int wide, const tc::Tiling* forced = nullptr) {
+        const std::vector<float>& g = w(ln + ".weight");
+        const std::vector<float>& b = w(ln + ".bias");
+        std::vector<float> Wg((size_t)N * K), cs(round_up(N, 4), 0.f), bw(round_up(N, 4), 0.f);
+        for (int n = 0; n < N; ++n) {
+            double s = 0.0, t = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const float v = W[(size_t)n * K + k] * g[k];
+                Wg[(size_t)n * K + k] = v;
+                s += (double)v;
+                t += (double)b[k] * (double)W[(size_t)n * K + k];
+            }
+            cs[n] = (float)s;
+            bw[n] = (float)t;
+        }
+        put_matrix(gw, Wg.data(), N, K, bias, wide, forced);
+        put(&gw.cs, cs);
+        put(&gw.bw, bw);
+    }
     // qkv projection with its output columns laid out [3][heads][hdp] (internal.h head_pad): rows of the reference
     // weight (3C, C) are moved to n' = (part*heads + h)*hdp + d, padding rows and their bias are zero
     void put_qkv(GemmWeight& gw, const std::string& wname, const std::string& bname, int C, int heads) {
@@ -242,9 +266,11 @@ struct Packer {
     // the same projection for the fused attention epilogue (tc_gemm.cuh): columns [head slot][q | k | v][hdp] in
     // sub-tiles of 144 = whole heads, zero rows / bias in the padding slots.  Returns false when the head width
     // does not divide the sub-tile (the layer then keeps the unfused qkv + window_attn_kernel pair).
-    bool put_qkv_heads(GemmWeight& gw, const std::string& wname, const std::string& bname, int C, int heads) {
+    bool put_qkv_heads(GemmWeight& gw, const std::string& wname, const std::string& bname, int C, int heads,
+                       GemmWeight* gp = nullptr, const std::string& lnname = std::string()) {
         const int hd = C / heads, hdp = head_pad(hd);
         gw = GemmWeight{};
+        if (gp) *gp = GemmWeight{};
         if (kAttnBN % (3 * hdp) != 0 || !attention_fusable(hd)) return false;
         const int hpb = kAttnBN / (3 * hdp);
         int nsubs = 0;
@@ -261,6 +287,7 @@ struct Packer {
                     Bp[np] = B[n];
                 }
         put_matrix(gw, Wp.data(), Np, C, &Bp, tc::kAttnE == 4 ? 1 : 0, &tl);
+        if (gp) put_ln_post(*gp, Wp.data(), Np, C, &Bp, lnname, tc::kAttnE == 4 ? 1 : 0, &tl);
         return true;
     }
     static float tf32_rna(float x) {           // cvt.rna.tf32.f32: nearest, ties away, 10 mantissa bits kept
@@ -335,9 +362,14 @@ static void pack_layer(Packer& P, int li) {
         P.put_ln(bw.n1, b + ".norm1", d.C);
         P.put_ln(bw.n2, b + ".norm2", d.C);
         P.put_qkv(bw.qkv, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
-        P.put_qkv_heads(bw.qkvh, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads);
+        P.put_qkv_heads(bw.qkvh, b + ".attn.qkv.weight", b + ".attn.qkv.bias", d.C, d.heads, &bw.qkvh_p, b + ".norm1");
         P.put_linear(bw.proj, b + ".attn.proj.weight", (b + ".attn.proj.bias").c_str(), kProjWide);
         P.put_linear(bw.fc1, b + ".mlp.linear_1.weight", (b + ".mlp.linear_1.bias").c_str(), kMlp1Wide);
+        {
+            const Weight& W1 = h->weights[h->index.at(b + ".mlp.linear_1.weight")];
+            P.put_ln_post(bw.fc1_p, W1.host.data(), (int)W1.shape[0], (int)W1.shape[1], &P.w(b + ".mlp.linear_1.bias"),
+                          b + ".norm2", kMlp1Wide);
+        }
         P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str(), kMlp2Wide);
         // relative-position bias gathered to [heads][16][16] (attention.py:190-205, 229-232)
         const std::vector<float>& table = P.w(b + ".attn.relative_position_bias_table");
@@ -353,9 +385,18 @@ static void pack_layer(Packer& P, int li) {
     if (d.scale == 1) {
         P.put_ln(lw.sn, d.prefix + ".subsample.norm", 2 * d.C);
         P.put_linear(lw.sub, d.prefix + ".subsample.down.weight", nullptr);
+        {
+            const Weight& Wd = h->weights[h->index.at(d.prefix + ".subsample.down.weight")];
+            P.put_ln_post(lw.sub_p, Wd.host.data(), (int)Wd.shape[0], (int)Wd.shape[1], nullptr, d.prefix + ".subsample.norm", 0);
+        }
     } else if (d.scale == 2) {
         P.put_ln(lw.sn, d.prefix + ".subsample.norm", d.C);
         P.put_linear(lw.sub, d.prefix + ".subsample.up.weight", nullptr, kSplitWide);
+        {
+            const Weight& Wu = h->weights[h->index.at(d.prefix + ".subsample.up.weight")];
+            P.put_ln_post(lw.sub_p, Wu.host.data(), (int)Wu.shape[0], (int)Wu.shape[1], nullptr, d.prefix + ".subsample.norm",
+                          kSplitWide);
+        }
     }
 }
 
@@ -740,6 +781,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.W = W;
     c.L.st = (cudaStream_t)stream;
     c.L.prof = h->prof;
+    c.L.ln_post = h->ln_post;
     c.L.tc = h->use_tc;
     c.L.pvq_tc = h->use_tc && h->pvq_tc;
     Bump dry(nullptr, 0);
@@ -806,6 +848,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (const char* e = getenv("ESCB_GEMM")) h->use_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
+    if (const char* e = getenv("ESCB_LN_POST")) h->ln_post = atoi(e);
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
     h->F = c.in_freq; h->n_fft = n_fft; h->win = c.win_length; h->hop = c.hop_length;

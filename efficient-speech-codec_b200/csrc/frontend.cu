@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace(), nullptr, nullptr}; }
 
 static size_t conv3_smem_bytes(int ld) { return (size_t)(kC3F + 2) * ((kC3T + 2) * ld + 4) * sizeof(float); }
 

@@ -26,6 +26,11 @@ struct LnParams {
     float eps;
     float2* stats;        // [M] (mean, rstd) scratch of the tcgen05 engine's ln_stats_kernel (unused by the SIMT engine)
     unsigned long long* trace;   // ESCB_TC_TRACE builds: 16 counters of this launch (null otherwise)
+    // post-GEMM LayerNorm (tc_gemm.cuh LNP): the weight image holds gamma-scaled rows W' = gamma o W and the epilogue
+    // computes rstd * (acc - mean * cs) + f * bw (+ bias), cs[n] = sum_k W'[n][k], bw[n] = sum_k beta[k] W[n][k],
+    // f = 0 for zero-padded rows (which bypass the norm in the reference)
+    const float* cs;
+    const float* bw;
 };
 
 // streaming 16-byte load: activations are read once per GEMM, so they bypass L1 allocation (ESCB_LDG_PLAIN: plain __ldg)
@@ -286,6 +291,8 @@ struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be nu
     const float* bias;
     int N, K, Kpad, ldw;
     TcWeight tc;
+    const float* cs;    // post-GEMM LayerNorm variants only (LnParams::cs / bw): column sums of the gamma-scaled weight
+    const float* bw;    //                                                        and beta . W
 };
 
 inline int pick_tn(int N) {

@@ -22,6 +22,7 @@ struct LnW { const float* g; const float* b; };     // padded to a multiple of 4
 struct BlockW {
     LnW n1, n2;
     GemmWeight qkv, proj, fc1, fc2;
+    GemmWeight qkvh_p, fc1_p;                        // gamma-folded images for the post-GEMM LayerNorm mode (tc.img null: not built)
     GemmWeight qkvh;                                 // qkv in head-major columns for the fused attention epilogue (tc.img null: not fusable)
     const float* relbias;                            // [heads][16][16], gathered from the (49, heads) table
 };
@@ -31,6 +32,7 @@ struct LayerW {
     BlockW blk[ESCB_MAX_DEPTH];
     LnW sn;
     GemmWeight sub;
+    GemmWeight sub_p;                                // PatchSplit weight, post-GEMM LayerNorm variant
 };
 
 struct QuantW {
@@ -68,12 +70,17 @@ static_assert(OP_COUNT == ESCB_NUM_OPS, "escb200.h ESCB_NUM_OPS out of date");
 struct ProfRec { cudaEvent_t a, b; int op; double flops, bytes; };
 struct Profiler { std::vector<ProfRec> recs; };
 
+// Post-GEMM LayerNorm (tc_gemm.cuh LNP) measured per class at 36 clips: PatchSplit 0.77 -> 0.65 ms, but the two
+// 8-producer-warp kernels are slower with it (fused attention 6.05 -> 6.47 ms, mlp1 5.36 -> 5.64 ms), so bits 4 and 8 are on (PatchMerge 0.75 -> 0.52 ms).
+constexpr int kLnPostDefault = 12;
+
 struct Launcher {                                    // stream + launch accounting + first-error latch
     cudaStream_t st = nullptr;
     long long launches = 0;
     cudaError_t err = cudaSuccess;
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
+    int ln_post = kLnPostDefault;                    // bit mask (ESCB_LN_POST): LayerNorm applied after the GEMM in 1 fused qkv+attention, 2 mlp1, 4 PatchSplit, 8 PatchMerge
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
     unsigned long long* trace = nullptr;             // ESCB_TC_TRACE builds: 16 counters per GEMM launch

@@ -5,7 +5,7 @@
 
 namespace escb {
 
-static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace(), nullptr, nullptr}; }
 
 void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, float* ze, int ldz) {
     AFrame al{enc, dec, q.in_freq, W, q.in_dim};

@@ -9,8 +9,10 @@
 
 namespace escb {
 
-static inline LnParams lnp(Launcher& L, const LnW& w) { return LnParams{w.g, w.b, kLnEps, L.ln_stats, L.next_trace()}; }
-static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace()}; }
+static inline LnParams lnp(Launcher& L, const LnW& w) { return LnParams{w.g, w.b, kLnEps, L.ln_stats, L.next_trace(), nullptr, nullptr}; }
+static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace(), nullptr, nullptr}; }
+// post-GEMM LayerNorm: statistics from the pre-kernel, column vectors of the gamma-folded weight
+static inline LnParams lnpost(Launcher& L, const GemmWeight& gw) { return LnParams{nullptr, nullptr, kLnEps, L.ln_stats, L.next_trace(), gw.cs, gw.bw}; }
 
 void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGeom& g, long long M, float* qkv, int ldq) {
     L.begin(OP_QKV, 2.0 * M * 3.0 * w.qkv.K * w.qkv.K, 4.0 * (1.0 * M * w.qkv.K + 3.0 * M * w.qkv.K));   // true dims (3C x C)
@@ -43,7 +45,11 @@ void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x
     case n: {                                                                                                       \
         using EP = EpiAttn<n, (n == 6 ? 6 : (n + 3) & ~3)>;                                                         \
         EP ep{att, ldo, w.qkvh.bias, w.relbias, heads, scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp, g.dW, g.dWw};             \
-        e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                                   \
+        if ((L.ln_post & 1) && w.qkvh_p.tc.img) {                                                                         \
+            ep.bias = w.qkvh_p.bias;                                                                                \
+            e = tc::launch<false, AWindow, EP, false, true>(L.st, al, lnpost(L, w.qkvh_p), w.qkvh_p, M, ep);        \
+        } else                                                                                                      \
+            e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                               \
     } break;
         ESCB_FUSED_HDS(X)
 #undef X
@@ -66,7 +72,10 @@ void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, 
     L.begin(OP_MLP1, 2.0 * M * w.fc1.N * w.fc1.K, 4.0 * M * (w.fc1.K + w.fc1.N));
     ARows al{x, ld};
     EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
-    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, kMlp1Wide != 0>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
+    if (L.tc && (L.ln_post & 2) && w.fc1_p.tc.img) {
+        ep.bias = w.fc1_p.bias;
+        ++L.launches, L.note(tc::launch<false, ARows, EpiRows<true, false>, kMlp1Wide != 0, true>(L.st, al, lnpost(L, w.fc1_p), w.fc1_p, M, ep));
+    } else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, kMlp1Wide != 0>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
 }
 
@@ -83,7 +92,9 @@ void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     EpiRows<false, false> ep{y, nullptr, nullptr, ldy, 0};
     const long long M = (long long)B * (H / 2) * W;
     L.begin(OP_MERGE, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
-    if (L.tc) ++L.launches, L.note(tc::launch<true, AMerge, EpiRows<false, false>>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+    if (L.tc && (L.ln_post & 8) && w.sub_p.tc.img)
+        ++L.launches, L.note(tc::launch<false, AMerge, EpiRows<false, false>, false, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
+    else if (L.tc) ++L.launches, L.note(tc::launch<true, AMerge, EpiRows<false, false>>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
     else L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 
@@ -92,7 +103,9 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     EpiSplit ep{y, ldy, H, W, w.out_dim};
     const long long M = (long long)B * H * W;
     L.begin(OP_SPLIT, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
-    if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide != 0>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+    if (L.tc && (L.ln_post & 4) && w.sub_p.tc.img)
+        ++L.launches, L.note(tc::launch<false, ARows, EpiSplit, kSplitWide != 0, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
+    else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide != 0>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 

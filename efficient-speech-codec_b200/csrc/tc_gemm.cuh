@@ -221,6 +221,29 @@ __device__ __forceinline__ void add_bias(float* v, const float* __restrict__ b) 
     }
 }
 
+// post-GEMM LayerNorm of N accumulator columns of one row: v = rstd * (v - mean * cs) + f * bw
+template <int N>
+__device__ __forceinline__ void ln_post(float* v, const float* __restrict__ cs, const float* __restrict__ bw, float mean,
+                                        float rstd, float f) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs) + c), b4 = __ldg(reinterpret_cast<const float4*>(bw) + c);
+            v[4 * c] = fmaf(rstd, fmaf(-mean, s4.x, v[4 * c]), f * b4.x);
+            v[4 * c + 1] = fmaf(rstd, fmaf(-mean, s4.y, v[4 * c + 1]), f * b4.y);
+            v[4 * c + 2] = fmaf(rstd, fmaf(-mean, s4.z, v[4 * c + 2]), f * b4.z);
+            v[4 * c + 3] = fmaf(rstd, fmaf(-mean, s4.w, v[4 * c + 3]), f * b4.w);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < N / 2; ++c) {
+            const float2 s2 = __ldg(reinterpret_cast<const float2*>(cs) + c), b2 = __ldg(reinterpret_cast<const float2*>(bw) + c);
+            v[2 * c] = fmaf(rstd, fmaf(-mean, s2.x, v[2 * c]), f * b2.x);
+            v[2 * c + 1] = fmaf(rstd, fmaf(-mean, s2.y, v[2 * c + 1]), f * b2.y);
+        }
+    }
+}
+
 // epilogues that run the window-attention core on the accumulator instead of storing it define kAttn
 template <class T, class = void> struct IsAttn { static constexpr bool value = false; };
 template <class T> struct IsAttn<T, decltype((void)T::kAttn)> { static constexpr bool value = true; };
@@ -254,7 +277,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 #define TC_ACC(slot, v)
 #endif
 
-template <bool LN, class AL, class EP, int E>
+template <bool LN, class AL, class EP, int E, bool LNP = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
                const int NB, const int resident, const int pf_dist) {
@@ -326,6 +349,10 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
             const long long mrow0 = (long long)(tile / ntn) * BM + q * 32;
             const long long m = mrow0 + lane;
+            float lmean = 0.f, lrstd = 0.f, lf = 0.f;      // post-GEMM LayerNorm of my row (zero-padded rows: all zero)
+            if constexpr (LNP) {
+                if (m < M) { const float2 t2 = __ldg(ln.stats + m); lmean = t2.x; lrstd = t2.y; lf = t2.y != 0.f ? 1.f : 0.f; }
+            }
             const int nrows = M - mrow0 >= 32 ? 32 : (M - mrow0 > 0 ? (int)(M - mrow0) : 0);   // rows of this quadrant that exist
             unsigned diff = 0;                             // keys of my window that lie in another shift region than me
             if (ep.masked) {
@@ -364,6 +391,10 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                         tmem_ld_cols<HDP>(th, qv);
                         tmem_ld_wait<HDP>(kv);
                         tmem_ld_wait<HDP>(qv);
+                        if constexpr (LNP) {
+                            ln_post<HDP>(kv, ln.cs + (bh - ep.bias) + HDP, ln.bw + (bh - ep.bias) + HDP, lmean, lrstd, lf);
+                            ln_post<HDP>(qv, ln.cs + (bh - ep.bias), ln.bw + (bh - ep.bias), lmean, lrstd, lf);
+                        }
                         add_bias<HDP>(kv, bh + HDP);
                         add_bias<HDP>(qv, bh);
                         __syncwarp();                      // the previous head's output rows have left the tile
@@ -413,6 +444,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                         float vv[HDP];
                         tmem_ld_cols<HDP>(th + 2 * HDP, vv);
                         tmem_ld_wait<HDP>(vv);
+                        if constexpr (LNP) ln_post<HDP>(vv, ln.cs + (bh - ep.bias) + 2 * HDP, ln.bw + (bh - ep.bias) + 2 * HDP, lmean, lrstd, lf);
                         add_bias<HDP>(vv, bh + 2 * HDP);
                         __syncwarp();                      // every lane is done with the K image
 #pragma unroll
@@ -502,6 +534,14 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 cr[i] = ectx[rr + 8 * i];
                 if (eok[rr + 8 * i]) okm |= 1u << i;
             }
+            float2 lst[LNP ? 4 : 1];                       // post-GEMM LayerNorm: (mean, rstd) of those rows
+            if constexpr (LNP) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long mr = (long long)(tile / ntn) * BM + q * 32 + rr + 8 * i;
+                    lst[i] = mr < M ? __ldg(ln.stats + mr) : make_float2(0.f, 0.f);
+                }
+            }
             for (int sub = 0; sub < nsub; ++sub) {
                 { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
                 tc_fence_after();
@@ -511,8 +551,9 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     // read, so their latency (L2 hits: the rows were prefetched a tile ahead) overlaps the staging
                     const int n = n0 + sub * BN + ch * 16 + c4 * 4;
                     const bool full4 = n + 3 < N;
-                    float4 b4 = zero4(), res[4];
+                    float4 b4 = zero4(), res[4], cs4 = zero4(), bw4 = zero4();
                     if (full4) {
+                        if constexpr (LNP) { cs4 = ldg4(ln.cs + n); bw4 = ldg4(ln.bw + n); }
                         b4 = ep.bias4(n);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) res[i] = ((okm >> i) & 1u) ? ep.resid4(cr[i], n) : zero4();
@@ -531,9 +572,22 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                         const int r = rr + 8 * i;
                         float4 o = *reinterpret_cast<const float4*>(stg + r * 16 + ((c4 ^ ((r >> 1) & 3)) << 2));
                         if (full4) {
+                            if constexpr (LNP) {
+                                const float mean = lst[i].x, rstd = lst[i].y, f = rstd != 0.f ? 1.f : 0.f;
+                                o.x = fmaf(rstd, fmaf(-mean, cs4.x, o.x), f * bw4.x);
+                                o.y = fmaf(rstd, fmaf(-mean, cs4.y, o.y), f * bw4.y);
+                                o.z = fmaf(rstd, fmaf(-mean, cs4.z, o.z), f * bw4.z);
+                                o.w = fmaf(rstd, fmaf(-mean, cs4.w, o.w), f * bw4.w);
+                            }
                             o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                             ep.fin4(cr[i], n, o, res[i]);
                         } else {
+                            if constexpr (LNP) {
+                                const float mean = lst[i].x, rstd = lst[i].y, f = rstd != 0.f ? 1.f : 0.f;
+                                o.x = fmaf(rstd, fmaf(-mean, __ldg(ln.cs + n), o.x), f * __ldg(ln.bw + n));
+                                if (n + 1 < N) o.y = fmaf(rstd, fmaf(-mean, __ldg(ln.cs + n + 1), o.y), f * __ldg(ln.bw + n + 1));
+                                if (n + 2 < N) o.z = fmaf(rstd, fmaf(-mean, __ldg(ln.cs + n + 2), o.z), f * __ldg(ln.bw + n + 2));
+                            }
                             ep.store(cr[i], n, o.x);
                             if (n + 1 < N) ep.store(cr[i], n + 1, o.y);
                             if (n + 2 < N) ep.store(cr[i], n + 2, o.z);
@@ -847,12 +901,12 @@ inline int sm_count() {
     return n;
 }
 
-template <bool LN, class AL, class EP, int E>
+template <bool LN, class AL, class EP, int E, bool LNP = false>
 inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, const TcWeight& w, long long M, const EP& ep) {
     using R = Roles<E, IsAttn<EP>::value>;
     static bool configured = false;     // per instantiation
     if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+        const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP, E, LNP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -870,24 +924,28 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
     static int pf_env = -2;
     if (pf_env == -2) { const char* e = getenv("ESCB_TC_PREFETCH"); pf_env = e ? atoi(e) : -1; }
     const int pf_dist = pf_env >= 0 ? pf_env : ((IsAttn<EP>::value || w.K >= 2 * w.N) ? 0 : 1);
-    tc_gemm_kernel<LN, AL, EP, E><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
+    tc_gemm_kernel<LN, AL, EP, E, LNP><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
     return cudaGetLastError();
 }
 
 // WIDE selects the 16-epilogue-warp role split (the weight must have been tiled with choose_tiling(.., wide = 1)).
-template <bool LN, class AL, class EP, bool WIDE = false>
+// LNP: the LayerNorm is applied after the GEMM (gw must hold the gamma-scaled image, ln.cs / ln.bw its vectors); the
+// producers then run the plain path (raw loads, no statistics / gamma / beta traffic, no normalisation arithmetic).
+template <bool LN, class AL, class EP, bool WIDE = false, bool LNP = false>
 inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
+    static_assert(!(LN && LNP), "LayerNorm is applied either in the producers or after the GEMM");
     const TcWeight& w = gw.tc;
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
     if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
     constexpr int E = IsAttn<EP>::value ? kAttnE : (WIDE ? 4 : 2);
     if ((w.wide != 0) != (E == 4)) return cudaErrorInvalidValue;
-    if (LN) {
+    if (LNP && (!ln.cs || !ln.bw)) return cudaErrorInvalidValue;
+    if (LN || LNP) {
         if (!ln.stats) return cudaErrorInvalidValue;
         const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
         if (e != cudaSuccess) return e;
     }
-    return launch_e<LN, AL, EP, E>(st, al, ln, w, M, ep);
+    return launch_e<LN, AL, EP, E, LNP>(st, al, ln, w, M, ep);
 }
 
 }  // namespace tc

@@ -230,10 +230,12 @@ def test_full_batch_properties(base0):
     assert maxabs(o.decode(co, fs)[0], audio[35].cpu()) <= AUDIO_TOL
 
 
-@pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"}])
+@pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"},
+                                 {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}])
 def test_engine_variants_agree(base0, env, monkeypatch):
-    """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair and the fp32 SIMT engine are
-    three implementations of the same layers: identical code indices, audio equal to fp32 reassociation noise
+    """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair, the fp32 SIMT engine and the
+    LayerNorm placement (in the A producers / after the GEMM on a gamma-folded weight) are alternative
+    implementations of the same layers: identical code indices, audio equal to fp32 reassociation noise
     (ragged width: padded windows + shift masks on every level)."""
     x = synth_audio(3, 16000 + 80 * 4 * 7, seed=41).cuda()
     codes0, fs0 = base0.encode(x, 6)
