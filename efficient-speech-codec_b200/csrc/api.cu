@@ -300,10 +300,23 @@ struct Packer {
     }
     // tcgen05 operand images from the packed Wt [Kpad][ldw] (see TcWeight in gemm.cuh)
     void put_tc(GemmWeight& gw, const std::vector<float>& t, int wide = 0, const tc::Tiling* forced = nullptr) {
-        TcWeight& w = gw.tc;
+        const tc::Tiling tl = forced ? *forced : tc::choose_tiling(gw.N, gw.K, wide);
+        put_tc_image(gw, gw.tc, t, wide, tl);
+        // Second tiling with one sub-tile per output tile (2-3x the tiles): picked at launch when the default one would
+        // leave most SMs idle in its last round (small row counts: the C = 384 / 192 levels at 36 clips), tc::pick.
+        gw.tc_alt = TcWeight{nullptr, gw.N, gw.K, 0, 0, 0, 0, 0, 0};
+        if (forced) return;
+        tc::Tiling alt = tl;
+        if (tl.nsub > 1) { alt.nsub = 1; alt.ntn = tl.ntn * tl.nsub; }
+        else if (tl.ntn == 1 && tl.BN >= 160) { alt.BN = ((gw.N + 1) / 2 + 15) / 16 * 16; alt.ntn = 2; }
+        else return;
+        const long long stage = (long long)alt.BN * 256;
+        alt.resident = (stage * alt.nkb <= tc::b_budget(wide) && alt.nkb <= tc::MAX_NB) ? 1 : 0;
+        put_tc_image(gw, gw.tc_alt, t, wide, alt);
+    }
+    void put_tc_image(const GemmWeight& gw, TcWeight& w, const std::vector<float>& t, int wide, const tc::Tiling& tl) {
         w.N = gw.N;
         w.K = gw.K;
-        const tc::Tiling tl = forced ? *forced : tc::choose_tiling(gw.N, gw.K, wide);
         w.wide = wide;
         w.ntn = tl.ntn;
         w.nsub = tl.nsub;

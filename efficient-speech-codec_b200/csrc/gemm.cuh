@@ -291,6 +291,7 @@ struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be nu
     const float* bias;
     int N, K, Kpad, ldw;
     TcWeight tc;
+    TcWeight tc_alt;    // the same weight cut into 2-3x as many (narrower) output tiles; img null: none
     const float* cs;    // post-GEMM LayerNorm variants only (LnParams::cs / bw): column sums of the gamma-scaled weight
     const float* bw;    //                                                        and beta . W
 };

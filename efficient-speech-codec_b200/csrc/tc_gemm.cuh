@@ -883,8 +883,12 @@ inline Tiling choose_tiling(int N, int K, int wide) {
 inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const int nkb = (K + KB - 1) / KB;
     const int max_sub = TMEM_COLS / 144;
-    const int ntn = (nsubs_total + max_sub - 1) / max_sub;
-    const int nsub = (nsubs_total + ntn - 1) / ntn;
+    // fewest padded (all-zero) sub-tiles first, then the most sub-tiles per output tile (A is produced once per tile)
+    int ntn = 1, nsub = 1, best_waste = 1 << 30;
+    for (int ns = max_sub; ns >= 1; --ns) {
+        const int nt = (nsubs_total + ns - 1) / ns, waste = nt * ns - nsubs_total;
+        if (waste < best_waste) { best_waste = waste; ntn = nt; nsub = ns; }
+    }
     const long long stage = 144LL * 256;
     const bool res = stage * nkb * nsub <= b_budget_attn() && nkb * nsub <= MAX_NB;
     if (ntn_out_subs) *ntn_out_subs = ntn * nsub;
@@ -929,12 +933,24 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
 }
 
 // WIDE selects the 16-epilogue-warp role split (the weight must have been tiled with choose_tiling(.., wide = 1)).
+// Tiling for this row count: the persistent grid runs ceil(tiles / SMs) rounds of the slowest CTA; with few row tiles
+// the narrower alternative (r times the tiles, each ~1/r of the work plus its own A production) needs fewer
+// round-equivalents, e.g. 169 row tiles of N = 384: 2 rounds vs 4 rounds of thirds.
+inline const TcWeight& pick(const GemmWeight& gw, long long M) {
+    if (!gw.tc_alt.img || !gw.tc.img) return gw.tc;
+    const long long ntm = (M + BM - 1) / BM, sms = sm_count();
+    const double r = (double)(gw.tc_alt.ntn * gw.tc_alt.nsub) / (double)(gw.tc.ntn);      // tiles ratio
+    const double cost_def = (double)((ntm * gw.tc.ntn + sms - 1) / sms);
+    const double cost_alt = (double)((ntm * gw.tc_alt.ntn + sms - 1) / sms) / r * 1.10;   // +10%: A produced r times
+    return cost_alt < cost_def ? gw.tc_alt : gw.tc;
+}
+
 // LNP: the LayerNorm is applied after the GEMM (gw must hold the gamma-scaled image, ln.cs / ln.bw its vectors); the
 // producers then run the plain path (raw loads, no statistics / gamma / beta traffic, no normalisation arithmetic).
 template <bool LN, class AL, class EP, bool WIDE = false, bool LNP = false>
 inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
     static_assert(!(LN && LNP), "LayerNorm is applied either in the producers or after the GEMM");
-    const TcWeight& w = gw.tc;
+    const TcWeight& w = pick(gw, M);
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
     if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
     constexpr int E = IsAttn<EP>::value ? kAttnE : (WIDE ? 4 : 2);
