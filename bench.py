@@ -300,6 +300,11 @@ def main_b200(args):
                  "share_of_step": tv["ms"] / tot_ms, "flop_per_byte": ai, "achieved_tflops": tflops, "achieved_gbs": gbs,
                  "peak_source": peaks["src"] + " (MEASURED_PEAKS.json bf16 sustained / hbm copy)",
                  "whole_step_tflops": value / N * GFLOP_PER_CLIP[args.config] / 1e3,
+                 # the step as a whole is tensor work (97 % of its flops are GEMM / conv): algorithmic TFLOP/s per GPU against
+                 # the TF32 ceiling (nominally half the measured bf16 rate) and against a third of it, the honest ceiling
+                 # of fp32-grade 3xTF32 products
+                 "whole_step_frac_of_tf32_peak": value / N * GFLOP_PER_CLIP[args.config] / 1e3 / (peaks["tensor"] / 2.0),
+                 "whole_step_frac_of_3xtf32_ceiling": value / N * GFLOP_PER_CLIP[args.config] / 1e3 / (peaks["tensor"] / 6.0),
                  "how": "escb_profile_begin/end: CUDA events around every launch on the launching stream, separate pass of the same K steps"})
     breakdown = {k: {"share": round(v["ms"] / tot_ms, 4), "ms_per_step": round(v["ms"] / args.steps, 4),
                      "launches_per_step": v["launches"] // args.steps,
