@@ -170,6 +170,30 @@ def test_pvq_streams_match_oracle(golden, base6):
     assert torch.equal(u.pvq_encode(3, z, None, 10), i64(golden["D_pvq3_codes"]))
 
 
+def test_pvq_streams_config4_1024_frames(base6):
+    """BASELINE configs[3]: the RVQ-only case, 1024 VQ frames (B = 1, W = 2048) through all 6 stream steps
+    (down-projection + argmin, then gather + up-projection + residual add) against the oracle."""
+    from oracle.esc_oracle import pvq_decode, pvq_encode
+    m, o = base6
+    u = Unit(m)
+    c = o.cfg
+    W = 2048
+    for q in range(6):
+        g = torch.Generator().manual_seed(100 + q)
+        C, Hq = c.quantizer_geometry(q)
+        enc = torch.randn(1, Hq * W, C, generator=g)
+        dec = None if q == 0 else torch.randn(1, Hq * W, C, generator=g)
+        resid = enc if dec is None else enc - dec
+        ref = pvq_encode(o.sd, f"quantizers.{q}", resid, Hq, c)
+        got = u.pvq_encode(q, enc, dec, W)
+        assert tuple(got.shape) == (1, 3, 1024)
+        assert torch.equal(got, ref), q
+        refd = pvq_decode(o.sd, f"quantizers.{q}", ref, Hq, c)
+        refd = refd if dec is None else refd + dec
+        gotd = u.pvq_decode(q, ref, dec, W, tuple(refd.shape))
+        assert maxabs(gotd, refd) <= 2e-6, q
+
+
 def test_codebook_argmin_bit_exact_and_ties(base6):
     """Codebook.quantize_to_code incl. rows that tie exactly: the lowest index must win."""
     from oracle.esc_oracle import codebook_argmin
