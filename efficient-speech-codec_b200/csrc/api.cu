@@ -286,8 +286,8 @@ struct Packer {
                     memcpy(&Wp[(size_t)np * C], &W[(size_t)n * C], (size_t)C * sizeof(float));
                     Bp[np] = B[n];
                 }
-        put_matrix(gw, Wp.data(), Np, C, &Bp, tc::kAttnE == 4 ? 1 : 0, &tl);
-        if (gp) put_ln_post(*gp, Wp.data(), Np, C, &Bp, lnname, tc::kAttnE == 4 ? 1 : 0, &tl);
+        put_matrix(gw, Wp.data(), Np, C, &Bp, tc::role_code(tc::kAttnE), &tl);
+        if (gp) put_ln_post(*gp, Wp.data(), Np, C, &Bp, lnname, tc::role_code(tc::kAttnE), &tl);
         return true;
     }
     static float tf32_rna(float x) {           // cvt.rna.tf32.f32: nearest, ties away, 10 mantissa bits kept

@@ -109,7 +109,7 @@ constexpr int kPvqUpWide = 1;      // product-VQ up-projection (K <= 96, N up to
 constexpr int kSplitWide = 1;      // PatchSplit GEMM role split
 constexpr int kProjWide = 1;       // attention output projection role split
 constexpr int kMlp2Wide = 0;       // mlp2 (K = 4N): 8 + 16 measured 4.65 ms, 16 + 8 5.01 ms
-constexpr int kMlp1Wide = 1;       // role split of the GELU GEMM: 1 = 16 epilogue + 8 producer warps, 0 = 8 + 16
+constexpr int kMlp1Wide = 2;       // role split of the GELU GEMM: 1 = 16 epilogue + 8 producer warps, 0 = 8 + 16
 constexpr int kEmbedMaxC = 64;     // patch_embed_kernel register budget: h_dims[0] <= 64
 constexpr int kEmbedMaxK = 16;     // 2 * patch_freq * patch_time <= 16
 

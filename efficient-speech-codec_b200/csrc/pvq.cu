@@ -35,7 +35,7 @@ void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int 
     EpiFrame ep{out, dec, q.in_freq, W, q.in_dim};
     const long long M = (long long)B * (W / 2);
     L.begin(OP_PVQ_UP, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim) + 24.0 * M);
-    if (L.pvq_tc) L.note(tc::launch<false, ACodes, EpiFrame, kPvqUpWide != 0>(L.st, al, noln(L), q.up, M, ep));
+    if (L.pvq_tc) L.note(tc::launch<false, ACodes, EpiFrame, kPvqUpWide>(L.st, al, noln(L), q.up, M, ep));
     else L.note(GemmLauncher<false, ACodes, EpiFrame, 8, 9>::launch(L.st, al, noln(L), q.up, M, ep));
 }
 

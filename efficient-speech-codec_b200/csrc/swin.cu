@@ -47,7 +47,7 @@ void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x
         EP ep{att, ldo, w.qkvh.bias, w.relbias, heads, scale, masked ? 1 : 0, g.nW, g.nWw, g.Hp, g.Wp, g.dW, g.dWw};             \
         if ((L.ln_post & 1) && w.qkvh_p.tc.img) {                                                                         \
             ep.bias = w.qkvh_p.bias;                                                                                \
-            e = tc::launch<false, AWindow, EP, false, true>(L.st, al, lnpost(L, w.qkvh_p), w.qkvh_p, M, ep);        \
+            e = tc::launch<false, AWindow, EP, 0, true>(L.st, al, lnpost(L, w.qkvh_p), w.qkvh_p, M, ep);        \
         } else                                                                                                      \
             e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                               \
     } break;
@@ -64,7 +64,7 @@ void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const floa
     L.begin(OP_PROJ, 2.0 * M * w.proj.N * w.proj.K, 4.0 * 3.0 * M * w.proj.K);
     ARows al{att, lda};
     EpiWindow ep{y, resid, w.proj.bias, ld, g};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow, kProjWide != 0>(L.st, al, noln(L), w.proj, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiWindow, kProjWide>(L.st, al, noln(L), w.proj, M, ep));
     else L.note(GemmLauncher<false, ARows, EpiWindow, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.proj, M, ep));
 }
 
@@ -74,8 +74,8 @@ void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, 
     EpiRows<true, false> ep{hid, w.fc1.bias, nullptr, ldh, 0};
     if (L.tc && (L.ln_post & 2) && w.fc1_p.tc.img) {
         ep.bias = w.fc1_p.bias;
-        ++L.launches, L.note(tc::launch<false, ARows, EpiRows<true, false>, kMlp1Wide != 0, true>(L.st, al, lnpost(L, w.fc1_p), w.fc1_p, M, ep));
-    } else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, kMlp1Wide != 0>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
+        ++L.launches, L.note(tc::launch<false, ARows, EpiRows<true, false>, kMlp1Wide, true>(L.st, al, lnpost(L, w.fc1_p), w.fc1_p, M, ep));
+    } else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiRows<true, false>, kMlp1Wide>(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiRows<true, false>, 6, 8, 9>::launch(L.st, al, lnp(L, w.n2), w.fc1, M, ep));
 }
 
@@ -83,7 +83,7 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
     L.begin(OP_MLP2, 2.0 * M * w.fc2.N * w.fc2.K, 4.0 * M * (w.fc2.K + 2.0 * w.fc2.N));
     ARows al{hid, ldh};
     EpiRows<false, true> ep{x, w.fc2.bias, x, ld, ld};
-    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>, kMlp2Wide != 0>(L.st, al, noln(L), w.fc2, M, ep));
+    if (L.tc) L.note(tc::launch<false, ARows, EpiRows<false, true>, kMlp2Wide>(L.st, al, noln(L), w.fc2, M, ep));
     else L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.fc2, M, ep));
 }
 
@@ -93,7 +93,7 @@ void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     const long long M = (long long)B * (H / 2) * W;
     L.begin(OP_MERGE, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
     if (L.tc && (L.ln_post & 8) && w.sub_p.tc.img)
-        ++L.launches, L.note(tc::launch<false, AMerge, EpiRows<false, false>, false, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
+        ++L.launches, L.note(tc::launch<false, AMerge, EpiRows<false, false>, 0, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
     else if (L.tc) ++L.launches, L.note(tc::launch<true, AMerge, EpiRows<false, false>>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
     else L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
@@ -104,8 +104,8 @@ void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     const long long M = (long long)B * H * W;
     L.begin(OP_SPLIT, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
     if (L.tc && (L.ln_post & 4) && w.sub_p.tc.img)
-        ++L.launches, L.note(tc::launch<false, ARows, EpiSplit, kSplitWide != 0, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
-    else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide != 0>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+        ++L.launches, L.note(tc::launch<false, ARows, EpiSplit, kSplitWide, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
+    else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
     else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 

@@ -58,7 +58,7 @@ struct Roles {
     static constexpr int EPI_WARPS = 4 * E;
     static constexpr int PROD_WARPS = 24 - EPI_WARPS;
     static constexpr int PROD_THREADS = PROD_WARPS * 32;
-    static constexpr int RPT = 32 / PROD_WARPS;            // rows per producer thread: 2 or 4
+    static constexpr int RPT = (32 + PROD_WARPS - 1) / PROD_WARPS;   // rows per producer thread: 2, 3 (12 warps: the last one only for r0 < 32) or 4
     static constexpr int ROW_STEP = 4 * PROD_WARPS;        // distance between a thread's rows
     static constexpr int DEPTH = 8 / RPT;                  // producer jobs with loads in flight
     static constexpr int NA = E == 4 ? 2 : 3;              // A ring slots
@@ -71,7 +71,11 @@ struct Roles {
     static constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
 };
 constexpr int kAttnE = 4;             // role split of the fused attention kernel: 16 epilogue warps
-inline int b_budget(int wide) { return wide ? Roles<4>::B_BUDGET : Roles<2>::B_BUDGET; }
+// role-split code stored with a packed weight (TcWeight::wide): 0 = 8 epilogue + 16 producer warps (E = 2),
+// 1 = 16 + 8 (E = 4), 2 = 12 + 12 (E = 3)
+constexpr int role_e(int wide) { return wide == 1 ? 4 : (wide == 2 ? 3 : 2); }
+constexpr int role_code(int e) { return e == 4 ? 1 : (e == 3 ? 2 : 0); }
+inline int b_budget(int wide) { return wide == 1 ? Roles<4>::B_BUDGET : (wide == 2 ? Roles<3>::B_BUDGET : Roles<2>::B_BUDGET); }
 inline int b_budget_attn() { return Roles<kAttnE, true>::B_BUDGET; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -609,6 +613,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
         // always in flight and tile boundaries cost nothing.  LayerNorm statistics come from ln_stats_kernel.
         const int pt = tid - PROD_BASE * 32;
         const int c = pt & 7, r0 = pt >> 3;
+        constexpr bool RAGGED = RPT * ROW_STEP != BM;      // 12 producer warps: row r0 + 2 * 48 exists only for r0 < 32
         struct Job { float4 a[RPT]; int k; unsigned m0, vm; };
         typename AL::Row myrow[RPT];
         unsigned cur_vm = 0, cur_m0 = 0;
@@ -622,21 +627,17 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 cur_vm = 0;
 #pragma unroll
                 for (int i = 0; i < RPT; ++i) {
-                    al.init((long long)cur_m0 + r0 + ROW_STEP * i, M, myrow[i]);
+                    const bool in_tile = !RAGGED || r0 + ROW_STEP * i < BM;
+                    al.init(in_tile ? (long long)cur_m0 + r0 + ROW_STEP * i : M, M, myrow[i]);      // m = M: an invalid row
                     if (al.valid(myrow[i])) cur_vm |= 1u << i;
                 }
                 const int next = ld_tile + pf_dist * gridDim.x;
-                if (pf_dist > 0 && next < ntiles && pt < 512) {           // pull the following tile's rows into L2 (four threads per row)
+                if (pf_dist > 0 && next < ntiles) {                       // pull the following tile's rows into L2 (four threads per row)
                     typename AL::Row pr;
-                    if (PROD_THREADS >= 512) {
-                        al.init((long long)(next / ntn) * BM + (pt >> 2), M, pr);
-                        if (al.valid(pr)) al.prefetch(pr, K, pt & 3);
-                    } else {                               // 256 producer threads: two rows each
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            al.init((long long)(next / ntn) * BM + (pt >> 2) + 64 * h, M, pr);
-                            if (al.valid(pr)) al.prefetch(pr, K, pt & 3);
-                        }
+                    for (int rr = pt >> 2; rr < BM; rr += PROD_THREADS / 4) {
+                        al.init((long long)(next / ntn) * BM + rr, M, pr);
+                        if (al.valid(pr)) al.prefetch(pr, K, pt & 3);
                     }
                 }
                 TC_ACC(3, ti_);
@@ -673,6 +674,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
                 const int r = r0 + ROW_STEP * i;
+                if (RAGGED && r >= BM) continue;
                 float4 v = j.a[i];
                 if (AL::kRawMask && !LN) v = mask4(v, k, K);      // (the LN branch masks after normalising)
                 if (LN && k < K && ((j.vm >> i) & 1u)) {
@@ -932,7 +934,7 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
     return cudaGetLastError();
 }
 
-// WIDE selects the 16-epilogue-warp role split (the weight must have been tiled with choose_tiling(.., wide = 1)).
+// WIDE is the role-split code (role_e) the weight was tiled with (choose_tiling(.., wide)).
 // Tiling for this row count: the persistent grid runs ceil(tiles / SMs) rounds of the slowest CTA; with few row tiles
 // the narrower alternative (r times the tiles, each ~1/r of the work plus its own A production) needs fewer
 // round-equivalents, e.g. 169 row tiles of N = 384: 2 rounds vs 4 rounds of thirds.
@@ -950,14 +952,14 @@ inline const TcWeight& pick(const GemmWeight& gw, long long M) {
 
 // LNP: the LayerNorm is applied after the GEMM (gw must hold the gamma-scaled image, ln.cs / ln.bw its vectors); the
 // producers then run the plain path (raw loads, no statistics / gamma / beta traffic, no normalisation arithmetic).
-template <bool LN, class AL, class EP, bool WIDE = false, bool LNP = false>
+template <bool LN, class AL, class EP, int WIDE = 0, bool LNP = false>
 inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
     static_assert(!(LN && LNP), "LayerNorm is applied either in the producers or after the GEMM");
     const TcWeight& w = pick(gw, M);
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
     if (M >= (1LL << 31)) return cudaErrorInvalidValue;      // loaders / epilogues use 32-bit row arithmetic
-    constexpr int E = IsAttn<EP>::value ? kAttnE : (WIDE ? 4 : 2);
-    if ((w.wide != 0) != (E == 4)) return cudaErrorInvalidValue;
+    constexpr int E = IsAttn<EP>::value ? kAttnE : role_e(WIDE);
+    if (w.wide != role_code(E)) return cudaErrorInvalidValue;
     if (LNP && (!ln.cs || !ln.bw)) return cudaErrorInvalidValue;
     if (LN || LNP) {
         if (!ln.stats) return cudaErrorInvalidValue;
