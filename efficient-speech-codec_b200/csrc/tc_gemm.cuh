@@ -70,7 +70,10 @@ struct Roles {
     static constexpr int TAIL_BYTES = STG_BYTES + CTX_BYTES + EPI_WARPS * 32 * 4 + NBARS * 8 + 16;
     static constexpr int B_BUDGET = SMEM_MAX - 1024 - NA * A_SLOT - TAIL_BYTES;
 };
-constexpr int kAttnE = 4;             // role split of the fused attention kernel: 16 epilogue warps
+#ifndef ESCB_ATTN_E
+#define ESCB_ATTN_E 4
+#endif
+constexpr int kAttnE = ESCB_ATTN_E;   // role split of the fused attention kernel: 4 = 16 epilogue + 8 producer warps (3 = 12 + 12)
 // role-split code stored with a packed weight (TcWeight::wide): 0 = 8 epilogue + 16 producer warps (E = 2),
 // 1 = 16 + 8 (E = 4), 2 = 12 + 12 (E = 3)
 constexpr int role_e(int wide) { return wide == 1 ? 4 : (wide == 2 ? 3 : 2); }
