@@ -105,11 +105,26 @@ struct Launcher {                                    // stream + launch accounti
 };
 
 constexpr float kLnEps = 1e-5f;
-constexpr int kPvqUpWide = 1;      // product-VQ up-projection (K <= 96, N up to 4608: all epilogue): 16 epilogue warps
-constexpr int kSplitWide = 1;      // PatchSplit GEMM role split
-constexpr int kProjWide = 1;       // attention output projection role split
-constexpr int kMlp2Wide = 0;       // mlp2 (K = 4N): 8 + 16 measured 4.65 ms, 16 + 8 5.01 ms
-constexpr int kMlp1Wide = 2;       // role split of the GELU GEMM: 1 = 16 epilogue + 8 producer warps, 0 = 8 + 16
+#ifndef ESCB_ROLE_PVQUP
+#define ESCB_ROLE_PVQUP 1
+#endif
+constexpr int kPvqUpWide = ESCB_ROLE_PVQUP;      // product-VQ up-projection (K <= 96, N up to 4608: all epilogue): 16 epilogue warps
+#ifndef ESCB_ROLE_SPLIT
+#define ESCB_ROLE_SPLIT 1
+#endif
+constexpr int kSplitWide = ESCB_ROLE_SPLIT;      // PatchSplit GEMM role split
+#ifndef ESCB_ROLE_PROJ
+#define ESCB_ROLE_PROJ 1
+#endif
+constexpr int kProjWide = ESCB_ROLE_PROJ;       // attention output projection role split
+#ifndef ESCB_ROLE_MLP2
+#define ESCB_ROLE_MLP2 0
+#endif
+constexpr int kMlp2Wide = ESCB_ROLE_MLP2;       // mlp2 (K = 4N): 8 + 16 measured 4.65 ms, 16 + 8 5.01 ms
+#ifndef ESCB_ROLE_MLP1
+#define ESCB_ROLE_MLP1 2
+#endif
+constexpr int kMlp1Wide = ESCB_ROLE_MLP1;       // role split of the GELU GEMM (codes: tc::role_e): 2 = 12 + 12 (5.14 ms), 1 = 16 epilogue + 8 producer warps (5.37), 0 = 8 + 16 (7.1)
 constexpr int kEmbedMaxC = 64;     // patch_embed_kernel register budget: h_dims[0] <= 64
 constexpr int kEmbedMaxK = 16;     // 2 * patch_freq * patch_time <= 16
 
