@@ -8,19 +8,22 @@
 // (the dropped lo*lo term is 2^-22 relative).  Weights are split once at escb_finalize(); activations are split
 // by the A-producer warps after the fused gather / LayerNorm.
 //
-// One persistent CTA per SM (832 threads), warp-specialised, looping over 128 x NT output tiles (NT <= 512):
-//   (warp ids as in the plain GEMMs; the fused attention kernel swaps the epilogue and producer ranges)
-//   warps 0-7   epilogue : tcgen05.ld a finished sub-tile (one TMEM lane quadrant x one column half per warp),
+// One persistent CTA per SM (832 threads), warp-specialised, looping over 128 x NT output tiles (NT <= 512).
+// 24 of the 26 warps are shared between the epilogue and the A producers in one of three splits (struct Roles:
+// 8 + 16, 12 + 12 or 16 + 8, chosen per layer class from measurements); shown here for 8 + 16, warp ids as in the plain
+// GEMMs (the fused attention kernel puts its epilogue warps above the producers):
+//   warps 0-7   epilogue : tcgen05.ld a finished sub-tile (one TMEM lane quadrant x one column share per warp),
 //                          transpose 32x16 chunks through a swizzled smem staging tile so that global stores and
-//                          residual loads are 64-byte row segments, apply bias / GELU / residual / scatter functor;
+//                          residual loads are 64-byte row segments, apply bias / GELU / residual / scatter functor -
+//                          or, for the fused qkv kernel, run the whole window-attention core on the accumulator;
 //   warps 8-23  producer : gather the logical A rows (window partition + cyclic shift, frequency-row pairing,
 //                          im2col ... loaders.cuh), LayerNorm, cvt.rna.tf32 split, write the hi / lo images of a
 //                          32-wide K block in the 128-byte-swizzled K-major layout into a 3-slot ring.  The
 //                          (tile, K block) jobs form one flat stream with the loads of four jobs in flight per
 //                          thread and the following tile prefetched into L2;
-//   warp 24     MMA      : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 3 per
-//                          k-step and sub-tile; tcgen05.commit releases the A slot / weight slot and publishes
-//                          each sub-tile's accumulator;
+//   warp 24     MMA      : one elected lane (elect.sync) issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN,
+//                          K=8) x 3 per k-step and sub-tile; tcgen05.commit releases the A slot / weight slot and
+//                          publishes each sub-tile's accumulator;
 //   warp 25     weights  : pre-swizzled [hi | lo] weight images, ONE cp.async.bulk (SASS UBLKCP) per (K block,
 //                          sub-tile).  Layers whose whole n-tile fits keep it RESIDENT in smem for the life of
 //                          the CTA; the others stream it through a 2..8 slot ring.
@@ -51,8 +54,9 @@ constexpr int MAX_NA = 3;
 constexpr int NBARS = 2 * MAX_NA + 2 * MAX_NB + 2 * MAX_REG;
 
 // Role split: E epilogue warps per TMEM lane quadrant.  E = 2: 8 epilogue + 16 producer warps, 3 A slots (the
-// default); E = 4: 16 epilogue + 8 producer warps, 2 A slots, for the GELU GEMM (small K, wide N) whose erf
-// epilogue would otherwise stall the tensor pipe.
+// default, producer-heavy layers such as mlp2); E = 4: 16 + 8, 2 A slots (epilogue-heavy layers: proj, PatchSplit,
+// the PVQ up-projection); E = 3: 12 + 12, where a producer thread owns rows r0, r0 + 48 and - for r0 < 32 only -
+// r0 + 96 (the GELU GEMM and the fused attention kernel, which are lopsided either way with 8 + 16 or 16 + 8).
 template <int E, bool ATTN = false>
 struct Roles {
     static constexpr int EPI_WARPS = 4 * E;
