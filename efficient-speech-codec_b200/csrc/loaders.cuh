@@ -386,7 +386,10 @@ struct EpiRows {   // Y[m*ldy + n] = act(v + bias[n]) (+ R[m*ldr + n])
     __device__ __forceinline__ void fin4(const Row& c, int n, float4 v, const float4 r) const {
         if (GELU) { gelu_erf2(v.x, v.y); gelu_erf2(v.z, v.w); }   // (scalar tails in store() use erff: same function to ~1e-7)
         if (RES) { v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w; }
-        *reinterpret_cast<float4*>(Y + c.y + n) = v;
+        // the MLP hidden map (4x the token map, read once by mlp2) is stored streaming so that it does not push the
+        // token map - mlp2's residual - out of L2
+        if (GELU) __stcs(reinterpret_cast<float4*>(Y + c.y + n), v);
+        else *reinterpret_cast<float4*>(Y + c.y + n) = v;
     }
     __device__ __forceinline__ void prefetch(const Row& c, int N) const {
         if (RES) for (int k = 0; k < N; k += 32) prefetch_l2(R + c.r + k);
