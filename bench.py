@@ -115,20 +115,42 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(cfg_name, budget_s, steps=None, warmup=1):
-    """Time the oracle port (encode + decode, S=6) on the host cores; returns (clips/s, info dict)."""
+def build_cpu_reference(cfg):
+    """(encode+decode callable, kind): the REAL reference staged under baseline/_ref (oracle/ref_loader.py) when it
+    travelled to this machine, else the pinned oracle port."""
     import torch
     from escb200.spec import CodecSpec
-    from escb200.synthetic import synth_audio, synth_state_dict
+    from escb200.synthetic import synth_state_dict
+    from oracle import ref_loader
+    sd = synth_state_dict(CodecSpec.from_kwargs(**cfg), 0)
+    model = None
+    try:
+        model = ref_loader.make_reference_model(cfg, sd)
+    except Exception as e:                                   # a broken staging must not kill the bench line
+        print(f"bench.py: reference import failed ({e!r}); timing the oracle port instead", file=sys.stderr)
+    if model is not None:
+        def run(x):
+            with torch.no_grad():
+                codes, fs = model.encode(x, 6)
+                return codes, model.decode(codes, fs)
+        return run, "reference", "yzGuu830/efficient-speech-codec esc.models.make_model(...).encode/decode (baseline/_ref), fp32 ATen"
     from oracle.esc_oracle import EscOracle
-    cfg = BASE if cfg_name == "base" else LARGE
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    o = EscOracle(cfg, synth_state_dict(CodecSpec.from_kwargs(**cfg), 0))
+    o = EscOracle(cfg, sd)
 
     def run(x):
         codes, fs = o.encode(x, 6)
-        return o.decode(codes, fs)
+        return codes, o.decode(codes, fs)
+    return run, "port", "oracle/esc_oracle.py (pinned restatement of the reference), fp32 ATen"
+
+
+def cpu_reference(cfg_name, budget_s, steps=None, warmup=1):
+    """Time the reference's CPU path (encode + decode, S=6) on the host cores; returns (clips/s, ms/step, info)."""
+    import torch
+    from escb200.synthetic import synth_audio
+    cfg = BASE if cfg_name == "base" else LARGE
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run, kind, what = build_cpu_reference(cfg)
 
     t0 = time.perf_counter()
     run(synth_audio(1, CLIP_SAMPLES, seed=0))               # warm-up + per-clip cost estimate
@@ -144,8 +166,9 @@ def cpu_reference(cfg_name, budget_s, steps=None, warmup=1):
     for _ in range(steps):
         run(x)
     dt = time.perf_counter() - t0
-    info = {"cores": cores, "kind": "port", "threads": torch.get_num_threads(),
-            "sample": f"{steps} x (encode+decode of {sample} synthetic 3 s clips, S=6), oracle/esc_oracle.py fp32 ATen"}
+    info = {"cores": cores, "kind": kind, "threads": torch.get_num_threads(),
+            "sample": f"{steps} x (encode+decode of {sample} synthetic 3 s clips, S=6; clips/s does not depend on the "
+                      f"sample's batch), {what}"}
     return sample * steps / dt, dt / steps * 1e3, info
 
 
@@ -163,11 +186,168 @@ def main_reference(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------------ B200 arm helpers
+def probe_tf32_peak(dev, seconds=0.6):
+    """Dense TF32 matmul rate of this GPU (cuBLAS through torch.matmul, allow_tf32=True, 8192^3, back to back)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters, best, t_end = 0, 0.0, time.perf_counter() + seconds
+        tot_ms = 0.0
+        while time.perf_counter() < t_end:
+            e0.record()
+            for _ in range(5):
+                a @ b
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            tot_ms += ms
+            iters += 5
+            best = max(best, 5 * 2.0 * n ** 3 / (ms * 1e-3) / 1e12)
+        return {"burst": best, "sustained": iters * 2.0 * n ** 3 / (tot_ms * 1e-3) / 1e12,
+                "how": "torch.matmul fp32 8192^3, torch.backends.cuda.matmul.allow_tf32=True, CUDA events"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def timed_ms(fn, iters, flush, dev):
+    """Mean device ms of fn() over `iters` calls, CUDA events on the current stream, L2 flushed between calls."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    return sum(a.elapsed_time(b) for a, b in ev) / iters
+
+
+def rvq_microbench(model, dev, flush, peaks, iters=20):
+    """BASELINE configs[3]: 1024 VQ frames (B=1, W=2048) through the six stream steps of ESC-Base, via the C ABI's
+    unit entry points.  (A) argmin only on pre-projected vectors; (B) the stream step enc, dec -> codes, dec_refine."""
+    import torch
+    from escb200 import native
+    lib, h, spec = native.lib(), model._handle(dev), model.spec
+    W, B = 2048, 1
+    T = W // spec.overlap
+    ws = model._ws(dev, h.workspace_bytes(B, W))
+    st = model._stream(dev)
+    g = torch.Generator().manual_seed(100)
+    streams = []
+    for q, qs in enumerate(spec.quantizers()):
+        C, Hq, d = qs.in_dim, qs.in_freq, qs.codebook_dim
+        enc = torch.randn(B, Hq * W, C, generator=g).to(dev)
+        dec = None if q == 0 else torch.randn(B, Hq * W, C, generator=g).to(dev)
+        z = [torch.randn(T, d, generator=g).to(dev) for _ in range(3)]
+        streams.append(dict(q=q, C=C, Hq=Hq, d=d, enc=enc, dec=dec, z=z, out=torch.empty_like(enc),
+                            codes=torch.empty((B, 3, T), dtype=torch.int64, device=dev),
+                            idx=torch.empty((T,), dtype=torch.int64, device=dev)))
+
+    def argmin_only():
+        for s in streams:
+            for grp in range(3):
+                native.check(lib.escb_codebook_argmin(h.ptr, s["q"], grp, native.ptr(s["z"][grp]), T, native.ptr(s["idx"]), st))
+
+    def stream_steps():
+        for s in streams:
+            native.check(lib.escb_pvq_encode(h.ptr, s["q"], native.ptr(s["enc"]), native.ptr(s["dec"]), B, W,
+                                             native.ptr(s["codes"]), native.ptr(ws), ws.numel(), st))
+            native.check(lib.escb_pvq_decode(h.ptr, s["q"], native.ptr(s["codes"]), native.ptr(s["dec"]), B, W,
+                                             native.ptr(s["out"]), native.ptr(ws), ws.numel(), st))
+
+    for _ in range(3):
+        argmin_only()
+        stream_steps()
+    l0 = h.launch_count()
+    ms_a = timed_ms(argmin_only, iters, flush, dev)
+    l1 = h.launch_count()
+    ms_b = timed_ms(stream_steps, iters, flush, dev)
+    l2 = h.launch_count()
+    sum_d = sum(s["d"] for s in streams)
+    bytes_a = T * (3 * 4 * sum_d + 6 * 3 * 8)                                   # SURVEY 8d: 1416 B / frame
+    flops_a = T * 2.0 * 3 * spec.codebook_size * sum_d                          # 0.651 MFLOP / frame
+    frame = [2 * s["C"] * s["Hq"] for s in streams]
+    bytes_b = T * (4 * (sum(frame) * 2 - frame[0]) + 4 * sum(frame) + 6 * 3 * 8)   # 169 104 B / frame
+    flops_b = flops_a + T * sum(2.0 * 2 * f * s["d"] for f, s in zip(frame, streams))
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    return {"workload": "ESC-Base RVQ only: 6 streams x 3 groups, 1024 VQ frames (B=1, W=2048), L2 flushed between iterations",
+            "argmin_only": {"ms": ms_a, "launches": (l1 - l0) // iters, "algorithmic_bytes": bytes_a,
+                            "achieved": bytes_a / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": bytes_a / (ms_a * 1e-3) / 1e9 / peaks["hbm"],
+                            "tflops": flops_a / (ms_a * 1e-3) / 1e12, "fp32_fma_peak_tflops_nominal": fp32_peak,
+                            "note": "460 flop/B: FP32-FMA / launch bound by construction, the HBM fraction is reported because the metric names it"},
+            "stream_step": {"ms": ms_b, "launches": (l2 - l1) // iters, "algorithmic_bytes": bytes_b,
+                            "achieved": bytes_b / (ms_b * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                            "frac": bytes_b / (ms_b * 1e-3) / 1e9 / peaks["hbm"], "tflops": flops_b / (ms_b * 1e-3) / 1e12,
+                            "bound": "hbm", "api": "escb_pvq_encode + escb_pvq_decode per stream"}}
+
+
+def incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, steps):
+    """The reference itself in eager PyTorch ON THIS GPU (fp32, TF32 off for matmul and cuDNN): the practical incumbent,
+    since the reference has no native kernels - plus the parity noise floor reference-CPU vs reference-GPU."""
+    import torch
+    from escb200.spec import CodecSpec
+    from escb200.synthetic import synth_state_dict
+    from oracle import ref_loader
+    try:
+        model = ref_loader.make_reference_model(cfg, synth_state_dict(CodecSpec.from_kwargs(**cfg), 0))
+    except Exception as e:
+        return {"unavailable": f"reference import failed: {e!r}"}
+    if model is None:
+        return {"unavailable": "baseline/_ref is not staged on this machine (oracle/ref_loader.py stage)"}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B = x_dev.shape[0]
+        with torch.no_grad():
+            n_cpu = min(2, B)
+            c_cpu, fs = model.encode(x_dev[:n_cpu].cpu(), 6)
+            a_cpu = model.decode(c_cpu, fs)
+            gm = model.to(dev)
+
+            def step():
+                c, f = gm.encode(x_dev, 6)
+                return c, gm.decode(c, f)
+            for _ in range(2):
+                c_gpu, a_gpu = step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = max(2, min(steps, 5))
+            e0.record()
+            for _ in range(n):
+                c_gpu, a_gpu = step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+                "what": "reference esc.ESC.encode+decode, eager PyTorch on this B200, fp32, allow_tf32=False (matmul and cuDNN)",
+                "noise_floor": {
+                    "clips": n_cpu, "codes_per_clip": int(c_cpu[0].numel()),
+                    "ref_cpu_vs_ref_gpu_code_mismatches": int((c_cpu != c_gpu[:n_cpu].cpu()).sum()),
+                    "ref_cpu_vs_ref_gpu_audio_max_abs": float((a_cpu - a_gpu[:n_cpu].cpu()).abs().max()),
+                    "escb200_vs_ref_cpu_code_mismatches": int((c_cpu != my_codes[:n_cpu].cpu()).sum()),
+                    "escb200_vs_ref_cpu_audio_max_abs": float((a_cpu - my_audio[:n_cpu].cpu()).abs().max()),
+                    "escb200_vs_ref_gpu_code_mismatches_all_clips": int((c_gpu != my_codes).sum())}}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def main_b200(args):
     import torch
     import torch.distributed as dist
     from escb200.codec import ESC
+    from escb200.parallel import gather_results, shard_bounds
     from escb200.spec import CodecSpec
     from escb200.synthetic import synth_audio, synth_state_dict
 
@@ -192,22 +372,24 @@ def main_b200(args):
     x_dev = x_host.to(dev)
     W = model.time_patches(CLIP_SAMPLES)
     n_out = spec.decoded_samples(W)
+    g_codes = g_audio = None
     if N > 1:
         g_codes = torch.empty((N * B, S, 3, W // 2), dtype=torch.int64, device=dev)
         g_audio = torch.empty((N * B, n_out), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # 2x the 126 MB L2
 
-    def step_device():
-        codes, fs = model.encode(x_dev, S)
+    def step_device(xd=x_dev, s=S, gather=True):
+        codes, fs = model.encode(xd, s)
         audio = model.decode(codes, fs)
-        if N > 1:
-            dist.all_gather_into_tensor(g_codes, codes)
-            dist.all_gather_into_tensor(g_audio, audio)
+        if N > 1 and gather:
+            gather_results(codes, audio, g_codes, g_audio)       # the one NCCL all-gather of the north star
         return codes, audio
 
     def step_host():
         codes, fs = model.encode(x_host, S)          # CPU tensors: pinned H2D + kernels + D2H inside
         audio = model.decode(codes, fs)
+        if N > 1:                                    # same workload as `value`: the gather of the device-side results
+            gather_results(codes.to(dev, non_blocking=True), audio.to(dev, non_blocking=True), g_codes, g_audio)
         return codes, audio
 
     def barrier():
@@ -223,26 +405,30 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed_steps(fn, k):
+        """K steps, each bracketed by CUDA events, L2 flushed (outside the event pairs) between steps; max over ranks."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        barrier()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+
     h = model._handle(dev)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
 
-    # ---- timed region: K steps, each bracketed by events, L2 flushed (outside the events) between steps
+    # ---- timed region
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = h.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in ev:
-        flush.zero_()
-        a.record()
-        step_device()
-        b.record()
-    barrier()
+    total_ms = timed_steps(step_device, args.steps)
     launches = h.launch_count() - launches0
     clocks = sampler.finish()
-    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
     value = N * B * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the public API with host tensors
@@ -257,7 +443,49 @@ def main_b200(args):
     codes_bytes = B * S * 3 * (W // 2) * 8
     e2e = {"value": N * B * args.steps / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": B * CLIP_SAMPLES * 4 + codes_bytes, "d2h_bytes_per_step": codes_bytes + B * n_out * 4,
-           "api": "ESC.encode(x_cpu, 6); ESC.decode(codes_cpu, feat_shape) -> escb_encode_host / escb_decode_host"}
+           "api": "ESC.encode(x_cpu, 6); ESC.decode(codes_cpu, feat_shape) -> escb_encode_host / escb_decode_host"
+                  + ("; + escb200.parallel.gather_results (NCCL)" if N > 1 else "")}
+
+    # ---- multi-rank result check: rank 0 recomputes the last rank's shard and compares it with its slice of the gather
+    gather_check = None
+    if N > 1:
+        codes_l, audio_l = step_device()
+        barrier()
+        if rank == 0:
+            r = N - 1
+            lo, hi = shard_bounds(N * B, r, N)
+            xr = synth_audio(B, CLIP_SAMPLES, seed=1000 + r).to(dev)
+            cr, ar = step_device(xr, S, gather=False)
+            ok = bool(torch.equal(g_codes[lo:hi], cr) and torch.equal(g_audio[lo:hi], ar)
+                      and torch.equal(g_codes[:B], codes_l) and torch.equal(g_audio[:B], audio_l))
+            gather_check = {"ok": ok, "what": f"rank 0 recomputed rank {r}'s shard: its codes and audio equal rows [{lo}, {hi}) "
+                                              "of the all-gathered tensors bit for bit; rank 0's own rows too"}
+            if not ok:
+                raise SystemExit("bench.py: all-gathered results differ from a local recomputation")
+        barrier()
+
+    # ---- strong scaling (BASELINE configs[4]): the same 288 clips whatever N is
+    strong = None
+    if args.config == "base" and args.strong_batch > 0 and args.strong_batch % N == 0:
+        Bs = args.strong_batch // N
+        lo, hi = shard_bounds(args.strong_batch, rank, N)
+        xs = torch.cat([synth_audio(1, CLIP_SAMPLES, seed=5000 + i) for i in range(lo, hi)]).to(dev)
+        gc = torch.empty((args.strong_batch, S, 3, W // 2), dtype=torch.int64, device=dev) if N > 1 else None
+        ga = torch.empty((args.strong_batch, n_out), dtype=torch.float32, device=dev) if N > 1 else None
+
+        def step_strong():
+            c, fs = model.encode(xs, S)
+            a = model.decode(c, fs)
+            if N > 1:
+                gather_results(c, a, gc, ga)
+        for _ in range(2):
+            step_strong()
+        k = max(2, min(args.steps, 5))
+        ms = timed_steps(step_strong, k)
+        strong = {"global_batch": args.strong_batch, "per_gpu_batch": Bs, "value": args.strong_batch * k / (ms * 1e-3),
+                  "unit": UNIT, "ms_per_step": ms / k, "steps": k, "scaling": "strong",
+                  "what": "BASELINE configs[4]: 288 clips sharded over the N ranks + one all-gather of codes and audio"}
+        del xs, gc, ga
 
     if N > 1:
         launches_t = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -269,8 +497,12 @@ def main_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel-class timing (rank 0, profiled pass: CUDA events around every launch on the launch stream)
+    # ================================================================================ rank 0 only from here
     peaks = load_peaks()
+    tf32 = probe_tf32_peak(dev)
+    peaks["tf32"] = tf32["sustained"]
+
+    # ---- per-kernel-class timing (profiled pass: CUDA events around every launch on the launch stream)
     h.profile_begin()
     for _ in range(args.steps):
         flush.zero_()
@@ -282,29 +514,39 @@ def main_b200(args):
     tflops = tv["flops"] / (tv["ms"] * 1e-3) / 1e12
     gbs = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
     ai = tv["flops"] / max(tv["bytes"], 1.0)
-    ridge = peaks["tensor"] * 1e3 / peaks["hbm"]
+    # Every tcgen05 class computes fp32-grade products as 3 TF32 MMAs, so its tensor ceiling is a third of the TF32
+    # peak and its ridge is (TF32 peak / 3) / HBM; the SIMT classes are bounded by the fp32 FMA rate.
+    simt = top in ("stft_gemm", "istft_gemm", "pvq_down_gemm", "codebook_argmin", "patch_embed", "deembed_conv3x3",
+                   "window_attention", "vq_loss", "layout")
+    ceil_t = (148 * 128 * 2 * 1.965e9 / 1e12) if simt else peaks["tf32"] / 3.0
+    ridge = ceil_t * 1e3 / peaks["hbm"]
     if ai >= ridge:
-        roof = {"bound": "tensor", "achieved": tflops, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tflops / peaks["tensor"]}
+        roof = {"bound": "tensor", "achieved": tflops, "peak": peaks["tf32"], "unit": "TFLOP/s", "frac": tflops / peaks["tf32"],
+                "frac_of_3xtf32_ceiling": tflops / (peaks["tf32"] / 3.0),
+                "peak_source": "TF32 dense matmul rate probed in this run (sustained); the honest ceiling of a 3xTF32 kernel is a third of it"}
     else:
-        roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
+        roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                "peak_source": peaks["src"] + " MEASURED_PEAKS.json hbm copy"}
     traffic, traffic_src = None, None
-    try:                                     # measured DRAM bytes per launch of that class (tools/ncu_traffic.py over one step)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if args.config == "base" and B == 36 and top in tj["classes"]:
-            traffic = tj["classes"][top]["dram_bytes_per_launch"]
-            traffic_src = "profiles/r1_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's launches of this class)"
-    except (OSError, ValueError, KeyError):
-        pass
+    for tf in ("r2_traffic.json", "r1_traffic.json"):
+        try:                                 # measured DRAM bytes per launch of that class (tools/ncu_traffic.py over one step)
+            tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if args.config == "base" and B == 36 and top in tj["classes"]:
+                traffic = tj["classes"][top]["dram_bytes_per_launch"]
+                traffic_src = f"profiles/{tf}: ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over one step's launches of this class (a committed capture of this build's step, not measured in this run)"
+                break
+        except (OSError, ValueError, KeyError):
+            pass
+    whole_tflops = value / N * GFLOP_PER_CLIP[args.config] / 1e3
     roof.update({"traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": tv["bytes"] / max(tv["launches"], 1),
+                 "algorithmic_flops_per_launch": tv["flops"] / max(tv["launches"], 1),
                  "kernel": top, "launches": tv["launches"], "avg_launch_ms": tv["ms"] / max(tv["launches"], 1),
-                 "share_of_step": tv["ms"] / tot_ms, "flop_per_byte": ai, "achieved_tflops": tflops, "achieved_gbs": gbs,
-                 "peak_source": peaks["src"] + " (MEASURED_PEAKS.json bf16 sustained / hbm copy)",
-                 "whole_step_tflops": value / N * GFLOP_PER_CLIP[args.config] / 1e3,
-                 # the step as a whole is tensor work (97 % of its flops are GEMM / conv): algorithmic TFLOP/s per GPU against
-                 # the TF32 ceiling (nominally half the measured bf16 rate) and against a third of it, the honest ceiling
-                 # of fp32-grade 3xTF32 products
-                 "whole_step_frac_of_tf32_peak": value / N * GFLOP_PER_CLIP[args.config] / 1e3 / (peaks["tensor"] / 2.0),
-                 "whole_step_frac_of_3xtf32_ceiling": value / N * GFLOP_PER_CLIP[args.config] / 1e3 / (peaks["tensor"] / 6.0),
+                 "share_of_step": tv["ms"] / tot_ms, "flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+                 "achieved_tflops": tflops, "achieved_gbs": gbs,
+                 "tf32_peak_tflops": tf32, "bf16_peak_tflops_measured": peaks["tensor"], "hbm_peak_gbs": peaks["hbm"],
+                 "whole_step_tflops": whole_tflops,
+                 "whole_step_frac_of_tf32_peak": whole_tflops / peaks["tf32"],
+                 "whole_step_frac_of_3xtf32_ceiling": whole_tflops / (peaks["tf32"] / 3.0),
                  "how": "escb_profile_begin/end: CUDA events around every launch on the launching stream, separate pass of the same K steps"})
     breakdown = {k: {"share": round(v["ms"] / tot_ms, 4), "ms_per_step": round(v["ms"] / args.steps, 4),
                      "launches_per_step": v["launches"] // args.steps,
@@ -313,13 +555,52 @@ def main_b200(args):
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if v["launches"]}
 
     def rvq_entry(names):
-        ms = sum(prof[n]["ms"] for n in names)
-        by = sum(prof[n]["bytes"] for n in names)
+        ms = sum(prof[n]["ms"] for n in names if n in prof)
+        by = sum(prof[n]["bytes"] for n in names if n in prof)
         return {"achieved": by / max(ms, 1e-9) / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": by / max(ms, 1e-9) / 1e6 / peaks["hbm"], "ms_per_step": ms / args.steps}
-    rvq = {"argmin_only": rvq_entry(["codebook_argmin"]),
-           "fused_stream_step": rvq_entry(["pvq_down_gemm", "codebook_argmin", "pvq_up_gemm"]),
+    rvq = {"in_step_b36": {"argmin_only": rvq_entry(["codebook_argmin"]),
+                           "stream_step": rvq_entry(["pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "pvq_stream_fused"])},
            "note": "argmin-only is FMA-issue bound by construction (460 flop/B, SURVEY 8d); the stream step is the HBM-bound one"}
+    extra = {}
+    if not args.quick:
+        if args.config == "base":
+            rvq["config4_1024_frames"] = rvq_microbench(model, dev, flush, peaks)
+        # ---- BASELINE configs[1] "all 6 bitrates swept": clips/s per num_streams
+        sweep = {}
+        for s in range(1, 7):
+            for _ in range(2):
+                step_device(x_dev, s, gather=False)
+            k = max(3, min(args.steps, 10))
+            ms = timed_steps(lambda s=s: step_device(x_dev, s, gather=False), k) if N == 1 else None
+            if ms is not None:
+                sweep[str(s)] = {"kbps": 1.5 * s, "value": B * k / (ms * 1e-3), "ms_per_step": ms / k}
+        extra["num_streams_sweep"] = {"unit": UNIT, "batch": B, "per_num_streams": sweep}
+        # ---- the reference in eager PyTorch on this GPU + parity noise floor
+        my_codes, my_audio = step_device(x_dev, S, gather=False)
+        extra["incumbent"] = incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, args.steps)
+        # ---- BASELINE configs[2]: ESC-Large, batch 64
+        if args.config == "base" and N == 1:
+            del my_codes, my_audio
+            lspec = CodecSpec.from_kwargs(**LARGE)
+            lm = ESC(**LARGE)
+            lm.load_state_dict(synth_state_dict(lspec, 0))
+            lm = lm.eval().to(dev)
+            xl = synth_audio(64, CLIP_SAMPLES, seed=2000).to(dev)
+
+            def step_large():
+                c, fs = lm.encode(xl, 6)
+                return lm.decode(c, fs)
+            for _ in range(3):
+                step_large()
+            k = max(3, min(args.steps, 5))
+            ms = timed_steps(step_large, k)
+            lt = 64 * k / (ms * 1e-3) * GFLOP_PER_CLIP["large"] / 1e3
+            extra["large_b64"] = {"workload": "BASELINE configs[2]: ESC-Large 9kbps, batch 64 x 3 s clips, num_streams=6, encode+decode",
+                                  "value": 64 * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k, "steps": k,
+                                  "whole_step_tflops": lt, "whole_step_frac_of_tf32_peak": lt / peaks["tf32"],
+                                  "whole_step_frac_of_3xtf32_ceiling": lt / (peaks["tf32"] / 3.0)}
+            del lm, xl
 
     cpu_v, _, cpu_info = cpu_reference(args.config, args.cpu_budget)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -331,6 +612,11 @@ def main_b200(args):
                        "l2": "256 MiB buffer written between timed steps (outside the event pairs)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "rvq": rvq,
             "cpu_baseline": dict(cpu_info, value=cpu_v, unit=UNIT), "kernels": breakdown}
+    if gather_check is not None:
+        line["gather_check"] = gather_check
+    if strong is not None:
+        line["strong_scaling"] = strong
+    line.update(extra)
     emit(line)
     if N > 1:
         dist.barrier()
@@ -347,6 +633,8 @@ def main():
     ap.add_argument("--config", default="base", choices=["base", "large"])
     ap.add_argument("--batch", type=int, default=36, help="clips per GPU")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--strong-batch", type=int, default=288, help="global batch of the strong-scaling line (0: skip)")
+    ap.add_argument("--quick", action="store_true", help="headline + roofline only (skip the sweep / microbench / incumbent / Large sections)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: `python bench.py --gpus N` re-launches itself one rank per GPU (the driver uses torchrun itself)

@@ -72,6 +72,8 @@ struct escb_handle {
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     unsigned long long* trace = nullptr;   // ESCB_TC_TRACE builds only
+    int* err_host = nullptr;   // host-mapped latch written by kernels that meet an out-of-range code index (ACodes)
+    int* err_dev = nullptr;    // the same word as the device sees it
     // grow-only scratch for the *_host entry points
     std::mutex host_mu;
     void* host_scratch = nullptr;
@@ -805,6 +807,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     Bump bp(ws, ws_bytes);
     plan(h, B, W, T, what, bp, c.wk);
     c.L.ln_stats = c.wk.stats;
+    c.L.code_err = h->err_dev;
 #ifdef ESCB_TC_TRACE
     c.L.trace = h->trace;
     if (h->trace) cudaMemsetAsync(h->trace, 0, 1024 * 16 * 8, c.L.st);
@@ -847,6 +850,10 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
         if (c.h_dims[l] < 1) return fail(ESCB_EINVAL, "h_dims[%d] must be positive", l);
         if (l < c.num_levels - 1 && (top >> l) % 2) return fail(ESCB_EINVAL, "odd frequency-patch counts are not supported");
         if (l > 0 && (c.h_dims[l] & 3)) return fail(ESCB_EINVAL, "h_dims[%d] must be a multiple of 4", l);
+        // LayerNorm rows are held in registers up to tc::LN_MAX_K floats (PatchMerge normalises 2 * h_dims[l])
+        if (c.h_dims[l] > tc::LN_MAX_K || (l < c.num_levels - 1 && 2 * c.h_dims[l] > tc::LN_MAX_K))
+            return fail(ESCB_EINVAL, "h_dims[%d]=%d is wider than the LayerNorm kernels support (%d, or %d below the last level)",
+                        l, c.h_dims[l], tc::LN_MAX_K, tc::LN_MAX_K / 2);
         if (!argmin_supported(c.codebook_dims[l]))
             return fail(ESCB_EINVAL, "codebook_dims[%d]=%d has no argmin kernel (6, 8, 12, 16, 24, 32)", l, c.codebook_dims[l]);
         if (c.codebook_size % 4) return fail(ESCB_EINVAL, "codebook_size must be a multiple of 4");
@@ -876,7 +883,9 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
         }
     }
     build_manifest(h);
-    cudaError_t e = swin_init();
+    cudaError_t e = cudaHostAlloc((void**)&h->err_host, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *h->err_host = 0; e = cudaHostGetDevicePointer((void**)&h->err_dev, h->err_host, 0); }
+    if (e == cudaSuccess) e = swin_init();
     if (e == cudaSuccess) e = frontend_init();
     if (e != cudaSuccess) {
         delete h;
@@ -890,6 +899,7 @@ void escb_destroy(escb_handle* h) {
     if (!h) return;
     if (h->arena) cudaFree(h->arena);
     if (h->host_scratch) cudaFree(h->host_scratch);
+    if (h->err_host) cudaFreeHost(h->err_host);
     delete h;
 }
 
@@ -1078,7 +1088,7 @@ int escb_decode_host(escb_handle* h, const int64_t* codes_host, int32_t B, int32
     e = cudaMemcpyAsync(audio_host, a_dev, (size_t)B * n_out * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(ESCB_ECUDA, "escb_decode_host: %s", cudaGetErrorString(e));
-    return ESCB_OK;
+    return escb_poll_error(h);
 }
 
 // ------------------------------------------------------------------------------------------------ unit entry points
@@ -1239,6 +1249,15 @@ extern "C" __attribute__((visibility("default"))) int escb_debug_trace(escb_hand
     return 0;
 }
 #endif
+
+int escb_poll_error(escb_handle* h) {
+    if (!h) return fail(ESCB_EINVAL, "null handle");
+    if (h->err_host && *(volatile int*)h->err_host) {
+        *(volatile int*)h->err_host = 0;
+        return fail(ESCB_EINVAL, "code index out of range [0, %d): the row was decoded as index 0", h->cfg.codebook_size);
+    }
+    return ESCB_OK;
+}
 
 int64_t escb_launch_count(const escb_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
 

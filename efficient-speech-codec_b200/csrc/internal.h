@@ -83,6 +83,7 @@ struct Launcher {                                    // stream + launch accounti
     int ln_post = kLnPostDefault;                    // bit mask (ESCB_LN_POST): LayerNorm applied after the GEMM in 1 fused qkv+attention, 2 mlp1, 4 PatchSplit, 8 PatchMerge
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
+    int* code_err = nullptr;                         // device view of the handle's host-mapped bad-code latch (ACodes)
     unsigned long long* trace = nullptr;             // ESCB_TC_TRACE builds: 16 counters per GEMM launch
     int trace_n = 0;
     unsigned long long* next_trace() { return trace ? trace + 16 * (size_t)(trace_n++ % 1024) : nullptr; }

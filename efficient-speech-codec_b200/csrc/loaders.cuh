@@ -222,14 +222,24 @@ struct ACodes {
     const long long* codes;
     const float* tables;   // [3][K][d] raw
     int S, s, T, d, ncodes;
+    int* bad;              // host-mapped error latch (escb_poll_error): set when a code index is outside [0, ncodes)
     struct Row { int c0, c1, c2; };
+    // The codes are caller data (saved encoded_*.pth files): an index outside the table would be an out-of-bounds read
+    // where the reference's F.embedding raises, so it is clamped to entry 0 and latched for the host to report.
+    __device__ __forceinline__ int checked(long long c) const {
+        if (c < 0 || c >= (long long)ncodes) {
+            if (bad) *(volatile int*)bad = 1;
+            return 0;
+        }
+        return (int)c;
+    }
     __device__ __forceinline__ void init(long long m, long long M, Row& r) const {
         r.c0 = -1; r.c1 = r.c2 = 0;
         if (m < M) {
             const int t = (int)(m % T);
             const long long b = m / T;
             const long long* p = codes + ((b * S + s) * 3) * (long long)T + t;
-            r.c0 = (int)p[0]; r.c1 = (int)p[T]; r.c2 = (int)p[2 * (long long)T];
+            r.c0 = checked(p[0]); r.c1 = checked(p[T]); r.c2 = checked(p[2 * (long long)T]);
         }
     }
     __device__ __forceinline__ bool valid(const Row& r) const { return r.c0 >= 0; }

@@ -31,7 +31,7 @@ void op_pvq_down(Launcher& L, const QuantW& q, const float* enc, const float* de
 
 void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
                float* out) {
-    ACodes al{codes, q.raw, S, s, W / 2, q.d, q.ncodes};
+    ACodes al{codes, q.raw, S, s, W / 2, q.d, q.ncodes, L.code_err};
     EpiFrame ep{out, dec, q.in_freq, W, q.in_dim};
     const long long M = (long long)B * (W / 2);
     L.begin(OP_PVQ_UP, 2.0 * M * q.frame_dim * q.d, 4.0 * M * ((dec ? 2.0 : 1.0) * q.frame_dim) + 24.0 * M);

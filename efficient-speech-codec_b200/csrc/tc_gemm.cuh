@@ -35,6 +35,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "gemm.cuh"
 
 namespace escb {
@@ -904,24 +906,34 @@ inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     return Tiling{144, nsub, ntn, nkb, res ? 1 : 0};
 }
 
+// Per-device caches: a process may drive several GPUs (codec.py keeps one handle per device), and both the SM count
+// and cudaFuncAttributeMaxDynamicSharedMemorySize are per-device properties.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static std::atomic<int> n[kMaxDevices];
+    const int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev].store(v, std::memory_order_relaxed);
     }
-    return n;
+    return v;
 }
 
 template <bool LN, class AL, class EP, int E, bool LNP = false>
 inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, const TcWeight& w, long long M, const EP& ep) {
     using R = Roles<E, IsAttn<EP>::value>;
-    static bool configured = false;     // per instantiation
-    if (!configured) {
+    static std::atomic<bool> configured[kMaxDevices];     // per instantiation and device
+    const int dev = current_device();
+    if (!configured[dev].load(std::memory_order_acquire)) {
         const cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LN, AL, EP, E, LNP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev].store(true, std::memory_order_release);
     }
     const long long stage = (long long)w.BN * 256;
     const int NB = w.resident ? w.nkb * w.nsub : (int)(R::B_BUDGET / stage < MAX_NB ? R::B_BUDGET / stage : MAX_NB);

@@ -87,6 +87,8 @@ class ESC(nn.Module):
             self._register(e.key, _init_tensor(e, self.spec), e.buffer)
         self._handles: Dict[torch.device, native.Handle] = {}
         self._synced: Dict[torch.device, tuple] = {}
+        self._tensors: Optional[list] = None         # [(checkpoint key, tensor)] in the native manifest's order
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.refresh_weights())
         self._workspace: Dict[torch.device, torch.Tensor] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
 
@@ -111,6 +113,20 @@ class ESC(nn.Module):
             raise RuntimeError("esc-b200 has no CPU fallback: a CUDA device (B200, sm_100a) is required")
         return torch.device("cuda", torch.cuda.current_device())
 
+    def refresh_weights(self) -> None:
+        """Force a re-pack of the native weight images on the next call.
+
+        ``_handle`` notices re-assigned tensors (``.to()``, ``load_state_dict``) and in-place autograd-visible updates
+        through ``(data_ptr, _version)``; writes that bypass the version counter (``p.data.copy_()``, EMA weight
+        surgery) are invisible to it - call this after such a write."""
+        self._tensors = None
+        self._synced.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)         # .to() / .cuda() / .float(): the tensors are replaced
+        self._tensors = None
+        return out
+
     def _handle(self, dev: torch.device) -> native.Handle:
         """Handle for ``dev`` with the module's current tensors loaded (re-packed only when they changed)."""
         h = self._handles.get(dev)
@@ -118,12 +134,14 @@ class ESC(nn.Module):
             with torch.cuda.device(dev):
                 h = native.Handle(self.spec)
             self._handles[dev] = h
-        sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
-        stamp = tuple((v.data_ptr(), v._version) for v in sd.values())
+        if self._tensors is None:                            # one state_dict() walk per weight change, not per call
+            sd = self.state_dict(keep_vars=True)
+            self._tensors = [(name, sd[name]) for name in h.weight_names()]
+        stamp = tuple((v.data_ptr(), v._version) for _, v in self._tensors)
         if self._synced.get(dev) != stamp:
             with torch.cuda.device(dev):
-                for name in h.weight_names():
-                    t = sd[name].detach()
+                for name, v in self._tensors:
+                    t = v.detach()
                     if t.dtype != torch.float32 or not t.is_contiguous():
                         t = t.float().contiguous()
                     if t.is_cuda and t.device != dev:
@@ -219,6 +237,9 @@ class ESC(nn.Module):
                 native.check(lib.escb_decode(h.ptr, native.ptr(cc), B, S, W, native.ptr(audio), None, native.ptr(ws),
                                              ws.numel(), self._stream(dev)))
             else:
+                # host codes come from saved encoded_*.pth files: same failure as F.embedding (codebook.py:53)
+                if codes.numel() and (int(codes.min()) < 0 or int(codes.max()) >= self.spec.codebook_size):
+                    raise IndexError("index out of range in self")
                 cin = self._host_in("codes_in", codes, torch.int64)
                 audio = torch.empty((B, n_out), dtype=torch.float32, pin_memory=True)
                 native.check(lib.escb_decode_host(h.ptr, native.ptr(cin), B, S, W, native.ptr(audio), self._stream(dev)))

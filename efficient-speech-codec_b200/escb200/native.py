@@ -26,6 +26,7 @@ EXPORTS = [
     "escb_workspace_bytes", "escb_encode", "escb_decode", "escb_forward", "escb_encode_host", "escb_decode_host",
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
+    "escb_poll_error",
 ]
 ESCB_NUM_OPS = 18
 
@@ -102,6 +103,7 @@ def lib() -> C.CDLL:
         "escb_pvq_decode": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, sz, vp]),
         "escb_codebook_argmin": (C.c_int, [vp, i32, i32, vp, i64, vp, vp]),
         "escb_launch_count": (i64, [vp]),
+        "escb_poll_error": (C.c_int, [vp]),
         "escb_profile_begin": (C.c_int, [vp]),
         "escb_profile_end": (C.c_int, [vp, C.POINTER(EscbOpStat), C.POINTER(i32)]),
     }
@@ -196,6 +198,10 @@ class Handle:
         b = C.c_size_t()
         check(self._lib.escb_workspace_bytes(self._h, batch, W, C.byref(b)))
         return b.value
+
+    def poll_error(self) -> None:
+        """Raise if a completed kernel met an out-of-range code index since the last poll (include/escb200.h)."""
+        check(self._lib.escb_poll_error(self._h))
 
     def launch_count(self) -> int:
         return self._lib.escb_launch_count(self._h)

@@ -191,6 +191,18 @@ typedef struct escb_op_stat {
 ESCB_API int escb_profile_begin(escb_handle* h);
 ESCB_API int escb_profile_end(escb_handle* h, escb_op_stat* stats /* [ESCB_NUM_OPS] */, int32_t* n);
 
+/* Code indices handed to escb_decode / escb_pvq_decode are caller data (saved .pth files).  An index outside
+ * [0, codebook_size) - where the reference's F.embedding raises IndexError (esc/modules/vq/codebook.py:53) - is
+ * decoded as index 0 (no out-of-bounds read) and latched; this call returns ESCB_EINVAL once if a kernel that has
+ * COMPLETED latched one since the last poll, else ESCB_OK.  escb_decode_host polls after its synchronisation. */
+ESCB_API int escb_poll_error(escb_handle* h);
+
+#ifdef ESCB_TC_TRACE
+/* Debug builds only (make trace): per-role cycle counters of the tcgen05 engine, 16 x 1024 u64 (tools/trace_step.py).
+ * First call allocates and arms the buffer; later calls synchronise and copy it to out_host. */
+ESCB_API int escb_debug_trace(escb_handle* h, unsigned long long* out_host);
+#endif
+
 /* Number of kernels the library has launched on behalf of this handle since creation (bench.py's gpu_launches). */
 ESCB_API int64_t escb_launch_count(const escb_handle* h);
 

@@ -300,6 +300,47 @@ def test_error_behaviour(base0):
     base0.eval()
 
 
+def test_out_of_range_codes_are_reported_not_read(base0):
+    """Codes are caller data (encoded_*.pth): F.embedding raises IndexError on the CPU (codebook.py:53); here host
+    tensors raise the same, device tensors are decoded with the bad index clamped and the error latched."""
+    from escb200 import native
+    x = synth_audio(1, 16000, seed=2)
+    codes, fs = base0.encode(x.cuda(), 6)
+    good = base0.decode(codes, fs)
+    for bad_value in (1024, -1, 1 << 40):
+        bad = codes.clone()
+        bad[0, 3, 1, 7] = bad_value
+        with pytest.raises(IndexError):
+            base0.decode(bad.cpu(), fs)
+        h = base0._handle(torch.device("cuda", torch.cuda.current_device()))
+        h.poll_error()                                   # clean before
+        out = base0.decode(bad, fs)                      # device path: asynchronous, must not fault
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        with pytest.raises(native.NativeError, match="out of range"):
+            h.poll_error()
+        h.poll_error()                                   # the latch clears
+    assert torch.equal(base0.decode(codes, fs), good)
+
+
+def test_weight_updates_are_picked_up(base0):
+    """_handle() re-packs on load_state_dict / versioned in-place updates, and refresh_weights() covers .data writes."""
+    m, sd = make_native(BASE, 0)
+    x = synth_audio(1, 16000, seed=2).cuda()
+    c0, _ = m.encode(x, 6)
+    assert torch.equal(c0, base0.encode(x, 6)[0])
+    sd6 = make_native(BASE, 6)[1]
+    m.load_state_dict(sd6)
+    c6, _ = m.encode(x, 6)
+    assert torch.equal(c6, make_native(BASE, 6)[0].encode(x, 6)[0]) and not torch.equal(c6, c0)
+    with torch.no_grad():
+        for k, v in m.state_dict(keep_vars=True).items():
+            if v.dtype == torch.float32:
+                v.data.copy_(sd[k].to(v.device))         # bypasses the version counter
+    m.refresh_weights()
+    assert torch.equal(m.encode(x, 6)[0], c0)
+
+
 def test_native_library_is_what_ran(base0):
     """The extension is loaded in-process and counted launches; nothing here can run on a fallback."""
     from escb200 import native

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "escb200.h")).read()
+    text = re.sub(r"#ifdef ESCB_TC_TRACE.*?#endif", "", text, flags=re.S)      # debug-build-only exports
     return re.findall(r"^ESCB_API [\w\* ]+?\b(escb_\w+)\(", text, flags=re.M)
 
 
