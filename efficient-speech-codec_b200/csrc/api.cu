@@ -1204,6 +1204,19 @@ int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, i
     return finish(c, "escb_codebook_argmin");
 }
 
+int escb_code_histogram(const int64_t* codes, int32_t B, int32_t S, int32_t G, int32_t T, int32_t ncodes, float* counts,
+                        void* stream) {
+    if (!codes || !counts) return fail(ESCB_EINVAL, "null argument");
+    if (B <= 0 || S <= 0 || G <= 0 || T <= 0 || ncodes <= 0)
+        return fail(ESCB_EINVAL, "codes must have shape (B, S, G, T) with positive extents");
+    if ((size_t)ncodes * sizeof(unsigned) > 48 * 1024) return fail(ESCB_EINVAL, "codebook_size too large for the histogram kernel");
+    Launcher L;
+    L.st = (cudaStream_t)stream;
+    op_code_histogram(L, (const long long*)codes, B, S, G, T, ncodes, counts);
+    if (L.err != cudaSuccess) return fail(ESCB_ECUDA, "escb_code_histogram: %s", cudaGetErrorString(L.err));
+    return ESCB_OK;
+}
+
 static const char* const kOpNames[OP_COUNT] = {
     "stft_gemm", "patch_embed", "qkv_gemm", "window_attention", "proj_gemm", "mlp1_gemm", "mlp2_gemm", "merge_gemm",
     "split_gemm", "pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "vq_loss", "deembed_conv5x5_gemm",

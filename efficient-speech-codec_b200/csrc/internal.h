@@ -151,6 +151,7 @@ void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const floa
                long long* out, int T, long long bstride);
 void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
                float* out);
+void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G, int T, int ncodes, float* counts);
 void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
                 int T, float* loss);
 

@@ -424,4 +424,29 @@ static __global__ void vq_loss_kernel(const float* __restrict__ ze, const int ld
     }
 }
 
+// ------------------------------------------------------------------------------------------------ code histogram
+// EntropyCounter.update (scripts/metrics.py:37-51 of the reference): counts[(s, g)][code] += occurrences over (b, t).
+// The reference builds a one-hot [B*T, 1024] tensor per (stream, group) and sums it; here one block per (stream,
+// group) histograms its B*T codes in shared memory and adds the 1024 bins to the running fp32 counts.  Indices
+// outside [0, ncodes) are skipped and latched (escb_poll_error), like ACodes.
+static __global__ void __launch_bounds__(256)
+code_histogram_kernel(const long long* __restrict__ codes, const int B, const int S, const int G, const int T,
+                      const int ncodes, float* __restrict__ counts, int* __restrict__ bad) {
+    extern __shared__ unsigned hist[];
+    const int sg = blockIdx.x, s = sg / G, g = sg - s * G;
+    for (int i = threadIdx.x; i < ncodes; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const long long n = (long long)B * T;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long b = i / T;
+        const int t = (int)(i - b * T);
+        const long long c = codes[((b * S + s) * G + g) * (long long)T + t];
+        if (c < 0 || c >= ncodes) { if (bad) *(volatile int*)bad = 1; continue; }
+        atomicAdd(&hist[(int)c], 1u);
+    }
+    __syncthreads();
+    float* out = counts + (long long)sg * ncodes;
+    for (int i = threadIdx.x; i < ncodes; i += blockDim.x) out[i] += (float)hist[i];
+}
+
 }  // namespace escb

@@ -74,4 +74,10 @@ void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const lo
     L.note(cudaGetLastError());
 }
 
+void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G, int T, int ncodes, float* counts) {
+    L.begin(OP_LAYOUT, 0.0, 8.0 * B * S * G * T + 8.0 * S * G * ncodes);
+    code_histogram_kernel<<<S * G, 256, (size_t)ncodes * sizeof(unsigned), L.st>>>(codes, B, S, G, T, ncodes, counts, L.code_err);
+    L.note(cudaGetLastError());
+}
+
 }  // namespace escb

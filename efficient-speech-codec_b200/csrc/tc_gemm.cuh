@@ -959,9 +959,9 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
 // round-equivalents, e.g. 169 row tiles of N = 384: 2 rounds vs 4 rounds of thirds.
 inline const TcWeight& pick(const GemmWeight& gw, long long M) {
     if (!gw.tc_alt.img || !gw.tc.img) return gw.tc;
-    static int force = -2;              // ESCB_TC_ALT=1 / 0 forces the narrow / default tiling (A-B debugging)
-    if (force == -2) { const char* e = getenv("ESCB_TC_ALT"); force = e ? atoi(e) : -1; }
-    if (force >= 0) return force ? gw.tc_alt : gw.tc;
+    // ESCB_TC_ALT=1 / 0 forces the narrow / default tiling (A-B debugging and the parity tests, which must be able to
+    // switch it inside one process: read per call)
+    if (const char* e = getenv("ESCB_TC_ALT")) { if (*e) return atoi(e) ? gw.tc_alt : gw.tc; }
     const long long ntm = (M + BM - 1) / BM, sms = sm_count();
     const double r = (double)(gw.tc_alt.ntn * gw.tc_alt.nsub) / (double)(gw.tc.ntn);      // tiles ratio
     const double cost_def = (double)((ntm * gw.tc.ntn + sms - 1) / sms);

@@ -3,6 +3,13 @@
     python -m scripts.compress --input ./audio.wav --save_path ./output --model_path ./esc9kbps \\
         --num_streams 6 --device cuda
 
+The argparse block and the body of ``main`` deliberately track the reference's CLI line for line (same flags, same help
+strings, same output names): this file IS the API surface the north star says to keep.  Deviations, all at the edges:
+``make_model`` is given ``model_name`` (the reference's one-argument call raises TypeError as shipped,
+scripts/compress.py:22 vs esc/models/codecs.py:190), the model is put in ``.eval()`` (there is no training path),
+wav I/O goes through scipy (torchaudio.load/save need torchcodec, absent here; the decoded wav is 32-bit float like
+``torchaudio.save`` of a float tensor), and ``--bitstream`` is an addition.
+
 Outputs are the reference's: ``decoded_{kbps}kbps_{name}`` (wav) and ``encoded_{kbps}kbps_{stem}.pth`` (the int64 code
 tensor, ``torch.save``).  ``--device cpu`` keeps the tensors on the host and stages them through the GPU (there is
 no CPU compute path)."""
@@ -25,6 +32,8 @@ def parse_args(argv=None):
     parser.add_argument("--model_path", type=str, required=True, help="folder contains model configuration and checkpoint")
     parser.add_argument("--num_streams", type=int, default=6, help="number of transmitted streams in encoding")
     parser.add_argument("--device", type=str, default="cpu")
+    parser.add_argument("--bitstream", action="store_true",
+                        help="(esc-b200 addition) also write encoded_*.escb: the codes packed at 10 bits per index")
     return parser.parse_args(argv)
 
 
@@ -47,6 +56,10 @@ def main(args):
         os.makedirs(args.save_path)
     save_wav(f"{args.save_path}/decoded_{args.num_streams*1.5}kbps_{fname}", recon_x, sr)
     torch.save(codes, f"{args.save_path}/encoded_{args.num_streams*1.5}kbps_{fname.split('.')[0]}.pth")
+    if getattr(args, "bitstream", False):
+        from escb200.bitstream import save_codes
+        save_codes(f"{args.save_path}/encoded_{args.num_streams*1.5}kbps_{fname.split('.')[0]}.escb", codes,
+                   cfg["model"].get("codebook_size", 1024))
     print(f"compression outputs saved into {args.save_path}")
     return codes, recon_x
 

@@ -177,6 +177,13 @@ ESCB_API int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes_dev
 ESCB_API int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z_dev, int64_t rows, int64_t* idx_dev,
                          void* stream);
 
+/* EntropyCounter.update of the evaluation sweep (scripts/metrics.py:37-51, fed by scripts/test.py:44); needs no
+ * handle (the counter is model-agnostic in the reference too):
+ *   codes_dev [B, S, G, T] int64 -> counts_dev [S*G, codebook_size] fp32, counts += occurrences (the caller zeroes
+ *   counts at EntropyCounter.reset_stats).  Indices outside [0, codebook_size) are not counted. */
+ESCB_API int escb_code_histogram(const int64_t* codes_dev, int32_t batch, int32_t num_streams, int32_t group_size,
+                        int32_t frames, int32_t codebook_size, float* counts_dev, void* stream);
+
 /* Per-kernel-class timing (bench.py's roofline figures).  Between escb_profile_begin and escb_profile_end every
  * kernel launched for this handle is bracketed by CUDA events on its stream; escb_profile_end synchronises the
  * device and returns, per class, the launch count, the summed device time and the summed ALGORITHMIC flops /

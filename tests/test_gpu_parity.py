@@ -274,6 +274,52 @@ def test_engine_variants_agree(base0, env, monkeypatch):
     assert maxabs(audio0.cpu(), audio1.cpu()) <= 2e-5
 
 
+@pytest.mark.parametrize("alt", ["", "0", "1"])
+def test_large_b64_config3(alt, monkeypatch):
+    """BASELINE configs[2]: ESC-Large at batch 64.  tc::pick switches weight tilings with the row count, so the B=64
+    launches run tilings the small-batch goldens never see: three clips against the oracle, batch invariance, and both
+    forced tilings (ESCB_TC_ALT, read per launch)."""
+    if alt:
+        monkeypatch.setenv("ESCB_TC_ALT", alt)
+    else:
+        monkeypatch.delenv("ESCB_TC_ALT", raising=False)
+    m, _ = make_native(LARGE, 2)
+    x = synth_audio(64, 48000, seed=77).cuda()
+    codes, fs = m.encode(x, 6)
+    audio = m.decode(codes, fs)
+    assert tuple(codes.shape) == (64, 6, 3, 150) and torch.isfinite(audio).all()
+    o = make_oracle(LARGE, 2)[0]
+    for b in ((0, 31, 63) if alt == "" else (63,)):
+        co, _ = o.encode(x[b:b + 1].cpu(), 6)
+        assert torch.equal(co[0], codes[b].cpu()), b
+        assert maxabs(o.decode(co, fs)[0], audio[b].cpu()) <= AUDIO_TOL
+    monkeypatch.delenv("ESCB_TC_ALT", raising=False)
+    c1, _ = m.encode(x[40:41], 6)                     # the same clip alone (different row count -> default tilings)
+    assert torch.equal(c1[0], codes[40])
+    assert maxabs(m.decode(c1, fs)[0].cpu(), audio[40].cpu()) <= 2e-5
+
+
+def test_eval_sweep_all_bitrates(base0, tmp_path):
+    """scripts.test.eval_epoch (reference scripts/test.py:22-55): model(x=x, x_feat=None, num_streams=s) for s = 1..6
+    with the device-side code histogram feeding EntropyCounter; utilisation equals the one-hot restatement on the codes."""
+    from scripts.metrics import SISDR, EntropyCounter
+    from scripts.test import eval_epoch
+    from test_formats_cpu import _reference_entropy
+    xs = synth_audio(4, 48000 - 80, seed=51)
+    loader = [xs[:2], xs[2:]]
+    ec = EntropyCounter(1024, num_streams=6, num_groups=3, device="cuda")
+    perf = eval_epoch(base0, loader, {"SISDR": SISDR()}, ec, "cuda", 1.5, num_streams=None, verbose=False)
+    assert len(perf["utilization"]) == 6 and len(perf["SISDR"]) == 6
+    codes6, _ = base0.encode(xs.cuda(), 6)
+    for s in range(1, 7):
+        rate, _ = _reference_entropy(codes6[:, :s].cpu(), 1024)
+        assert perf["utilization"][s - 1] == rate, s
+    # the counter after the last bitrate holds the S=6 histogram
+    _, util = ec.compute_utilization()
+    assert util == _reference_entropy(codes6.cpu(), 1024)[1]
+    assert float(ec._counts.sum()) == 6 * 3 * 4 * 150
+
+
 def test_host_buffer_path_equals_device_path(base0):
     """escb_encode_host / escb_decode_host (CPU tensors in, CPU tensors out) give the same bits."""
     x = synth_audio(3, 16000, seed=31)
