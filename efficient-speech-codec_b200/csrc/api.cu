@@ -69,6 +69,7 @@ struct escb_handle {
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
     int ln_post = kLnPostDefault;   // ESCB_LN_POST bit mask (internal.h)
+    bool fuse_mlp = true;      // ESCB_FUSE_MLP=0 keeps the unfused mlp1 + mlp2 pair everywhere (A/B debugging, variant tests)
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
     unsigned long long* trace = nullptr;   // ESCB_TC_TRACE builds only
@@ -349,6 +350,61 @@ struct Packer {
             }
         put(&w.img, out);
     }
+    // Operands of the fused MLP kernel (mlp_fused.cuh): per 64-column hidden chunk j the fc1 stages (K blocks of the
+    // input channels, rows = hidden units 64j..64j+63) followed by the two fc2 stages (K blocks = hidden units
+    // 64j + 32kb.., rows = output channels), each stage [hi image | lo image] in the 128-byte-swizzled K-major layout.
+    void put_mlp_fused(mf::Weights& mw, const std::string& b, int C) {
+        const Weight& W1 = h->weights[h->index.at(b + ".mlp.linear_1.weight")];     // (4C, C)
+        const Weight& W2 = h->weights[h->index.at(b + ".mlp.linear_2.weight")];     // (C, 4C)
+        const int hidden = (int)W1.shape[0];
+        mw = mf::Weights{};
+        const mf::Plan pl = mf::make_plan(C, hidden);
+        mw.plan = pl;
+        if (!pl.ok) return;
+        std::vector<float> img(pl.img_floats, 0.f);
+        auto put_el = [&](float* hi, float* lo, int r, int kk, float v) {
+            const float hv = tf32_rna(v);
+            const size_t pos = (size_t)r * 32 + (size_t)(((kk >> 2) ^ (r & 7)) << 2) + (kk & 3);
+            hi[pos] = hv;
+            lo[pos] = tf32_rna(v - hv);
+        };
+        for (int j = 0; j < pl.nch; ++j) {
+            float* chunk = img.data() + (size_t)j * pl.chunk_bytes / 4;
+            for (int kb = 0; kb < pl.nkb1; ++kb) {
+                float* hi = chunk + (size_t)kb * mf::ST1_BYTES / 4;
+                float* lo = hi + mf::HC * 32;
+                for (int r = 0; r < mf::HC; ++r) {
+                    const int n = j * mf::HC + r;
+                    if (n >= hidden) break;
+                    for (int kk = 0; kk < 32; ++kk) {
+                        const int k = kb * 32 + kk;
+                        if (k >= C) break;
+                        put_el(hi, lo, r, kk, W1.host[(size_t)n * C + k]);
+                    }
+                }
+            }
+            for (int kb = 0; kb < 2; ++kb) {
+                float* hi = chunk + ((size_t)pl.nkb1 * mf::ST1_BYTES + (size_t)kb * pl.st2_bytes) / 4;
+                float* lo = hi + (size_t)pl.N2 * 32;
+                for (int r = 0; r < C; ++r)
+                    for (int kk = 0; kk < 32; ++kk) {
+                        const int k = j * mf::HC + kb * 32 + kk;
+                        if (k >= hidden) break;
+                        put_el(hi, lo, r, kk, W2.host[(size_t)r * hidden + k]);
+                    }
+            }
+        }
+        std::vector<float> b1((size_t)pl.nch * mf::HC, 0.f), b2((size_t)pl.N2, 0.f), g((size_t)pl.Kp16, 0.f), be((size_t)pl.Kp16, 0.f);
+        memcpy(b1.data(), w(b + ".mlp.linear_1.bias").data(), (size_t)hidden * sizeof(float));
+        memcpy(b2.data(), w(b + ".mlp.linear_2.bias").data(), (size_t)C * sizeof(float));
+        memcpy(g.data(), w(b + ".norm2.weight").data(), (size_t)C * sizeof(float));
+        memcpy(be.data(), w(b + ".norm2.bias").data(), (size_t)C * sizeof(float));
+        put(&mw.img, img);
+        put(&mw.b1, b1);
+        put(&mw.b2, b2);
+        put(&mw.gamma, g);
+        put(&mw.beta, be);
+    }
     static void init_gemm(GemmWeight& gw, int N, int K, std::vector<float>& t) {
         gw.N = N;
         gw.K = K;
@@ -386,6 +442,7 @@ static void pack_layer(Packer& P, int li) {
                           b + ".norm2", kMlp1Wide);
         }
         P.put_linear(bw.fc2, b + ".mlp.linear_2.weight", (b + ".mlp.linear_2.bias").c_str(), kMlp2Wide);
+        P.put_mlp_fused(bw.mlpf, b, d.C);
         // relative-position bias gathered to [heads][16][16] (attention.py:190-205, 229-232)
         const std::vector<float>& table = P.w(b + ".attn.relative_position_bias_table");
         std::vector<float> rb((size_t)d.heads * 256);
@@ -681,8 +738,11 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
             op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, lw.hdp, C, nwin, (j & 1) != 0, g);
         }
         op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
-        op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
-        op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);
+        if (c.L.fuse_mlp && bw.mlpf.plan.ok) op_mlp_fused(c.L, bw, xw, ld, M, mf::StatsOut{});
+        else {
+            op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
+            op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);
+        }
         src = xw;
     }
     if (lw.scale == 1) op_merge(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim));
@@ -799,6 +859,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.L.ln_post = h->ln_post;
     c.L.tc = h->use_tc;
     c.L.pvq_tc = h->use_tc && h->pvq_tc;
+    c.L.fuse_mlp = h->use_tc && h->fuse_mlp;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -868,6 +929,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (const char* e = getenv("ESCB_GEMM")) h->use_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
+    if (const char* e = getenv("ESCB_FUSE_MLP")) h->fuse_mlp = atoi(e) != 0;
     if (const char* e = getenv("ESCB_LN_POST")) h->ln_post = atoi(e);
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
@@ -1220,7 +1282,7 @@ int escb_code_histogram(const int64_t* codes, int32_t B, int32_t S, int32_t G, i
 static const char* const kOpNames[OP_COUNT] = {
     "stft_gemm", "patch_embed", "qkv_gemm", "window_attention", "proj_gemm", "mlp1_gemm", "mlp2_gemm", "merge_gemm",
     "split_gemm", "pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "vq_loss", "deembed_conv5x5_gemm",
-    "deembed_conv3x3", "istft_gemm", "layout", "qkv_attention_fused"};
+    "deembed_conv3x3", "istft_gemm", "layout", "qkv_attention_fused", "mlp_fused"};
 
 int escb_profile_begin(escb_handle* h) {
     if (!h) return fail(ESCB_EINVAL, "null handle");

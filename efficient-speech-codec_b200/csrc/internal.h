@@ -9,6 +9,7 @@
 #include "gemm.cuh"
 #include "loaders.cuh"
 #include "tc_gemm.cuh"
+#include "mlp_fused.h"
 
 namespace escb {
 
@@ -25,6 +26,7 @@ struct BlockW {
     GemmWeight qkvh_p, fc1_p;                        // gamma-folded images for the post-GEMM LayerNorm mode (tc.img null: not built)
     GemmWeight qkvh;                                 // qkv in head-major columns for the fused attention epilogue (tc.img null: not fusable)
     const float* relbias;                            // [heads][16][16], gathered from the (49, heads) table
+    mf::Weights mlpf;                                // fused LN2 -> fc1 -> GELU -> fc2 -> +x kernel (plan.ok == 0: not built, C > 96)
 };
 
 struct LayerW {
@@ -63,7 +65,7 @@ struct FrontW {
 // Kernel classes for launch accounting / per-op timing (escb_profile_begin/end).
 enum OpId {
     OP_STFT, OP_EMBED, OP_QKV, OP_ATTN, OP_PROJ, OP_MLP1, OP_MLP2, OP_MERGE, OP_SPLIT, OP_PVQ_DOWN, OP_ARGMIN,
-    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_QKV_ATTN, OP_COUNT
+    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_QKV_ATTN, OP_MLP_FUSED, OP_COUNT
 };
 static_assert(OP_COUNT == ESCB_NUM_OPS, "escb200.h ESCB_NUM_OPS out of date");
 
@@ -80,6 +82,7 @@ struct Launcher {                                    // stream + launch accounti
     cudaError_t err = cudaSuccess;
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
+    bool fuse_mlp = true;                            // LN2 -> fc1 -> GELU -> fc2 -> +x in one launch where a plan exists (ESCB_FUSE_MLP=0: the unfused pair)
     int ln_post = kLnPostDefault;                    // bit mask (ESCB_LN_POST): LayerNorm applied after the GEMM in 1 fused qkv+attention, 2 mlp1, 4 PatchSplit, 8 PatchMerge
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
     float2* ln_stats = nullptr;                      // [max rows] LayerNorm statistics scratch (tc engine)
@@ -140,6 +143,7 @@ void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const floa
              const WindowGeom& g, long long M);
 void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, float* hid, int ldh);
 void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long M, float* x, int ld);
+void op_mlp_fused(Launcher& L, const BlockW& w, float* x, int ld, long long M, const mf::StatsOut& so);
 void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
 void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
 cudaError_t swin_init();

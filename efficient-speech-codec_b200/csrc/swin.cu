@@ -87,6 +87,14 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
     else L.note(GemmLauncher<false, ARows, EpiRows<false, true>, 3, 5, 6, 8, 9>::launch(L.st, al, noln(L), w.fc2, M, ep));
 }
 
+// LN2 -> fc1 -> GELU -> fc2 -> +x in one launch (mlp_fused.cuh); x is updated in place
+void op_mlp_fused(Launcher& L, const BlockW& w, float* x, int ld, long long M, const mf::StatsOut& so) {
+    const double C = w.fc1.K, Hd = w.fc1.N;
+    L.begin(OP_MLP_FUSED, 4.0 * M * C * Hd, 4.0 * 2.0 * M * C);          // both GEMMs; x in, x out
+    cudaError_t e = ld == w.mlpf.plan.ld ? mf::launch(L.st, w.mlpf, x, M, kLnEps, so) : cudaErrorInvalidValue;
+    L.note(e);
+}
+
 void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {
     AMerge al{x, ld, H, W, w.C};
     EpiRows<false, false> ep{y, nullptr, nullptr, ldy, 0};

@@ -28,7 +28,7 @@ EXPORTS = [
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
     "escb_poll_error", "escb_code_histogram",
 ]
-ESCB_NUM_OPS = 18
+ESCB_NUM_OPS = 19
 
 
 class NativeLibraryMissing(ImportError):

@@ -37,7 +37,7 @@ extern "C" {
 #define ESCB_ABI_VERSION 1
 #define ESCB_MAX_LEVELS 8
 #define ESCB_MAX_DEPTH 8
-#define ESCB_NUM_OPS 18
+#define ESCB_NUM_OPS 19
 
 enum {
     ESCB_OK = 0,

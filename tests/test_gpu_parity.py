@@ -255,9 +255,11 @@ def test_full_batch_properties(base0):
 
 
 @pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"},
-                                 {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}])
+                                 {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}, {"ESCB_FUSE_MLP": "0"},
+                                 {"ESCB_FUSE_MLP": "0", "ESCB_FUSE_ATTN_MAXC": "0"}])
 def test_engine_variants_agree(base0, env, monkeypatch):
-    """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair, the fp32 SIMT engine and the
+    """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair, the fp32 SIMT engine, the fused
+    MLP kernel (LN2 -> fc1 -> GELU -> fc2 -> +x in one launch, the default for C <= 96) against the mlp1 + mlp2 pair, and the
     LayerNorm placement (in the A producers / after the GEMM on a gamma-folded weight) are alternative
     implementations of the same layers: identical code indices, audio equal to fp32 reassociation noise
     (ragged width: padded windows + shift masks on every level)."""
