@@ -69,6 +69,7 @@ struct escb_handle {
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
     int ln_post = kLnPostDefault;   // ESCB_LN_POST bit mask (internal.h)
+    bool emit_stats = true;    // ESCB_EMIT_STATS=0: every LayerNorm GEMM runs its own statistics pre-kernel (A/B debugging)
     bool fuse_mlp = true;      // ESCB_FUSE_MLP=0 keeps the unfused mlp1 + mlp2 pair everywhere (A/B debugging, variant tests)
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
@@ -370,21 +371,29 @@ struct Packer {
         };
         for (int j = 0; j < pl.nch; ++j) {
             float* chunk = img.data() + (size_t)j * pl.chunk_bytes / 4;
+            const bool packed = mf::fc1_tail_packed(C);
             for (int kb = 0; kb < pl.nkb1; ++kb) {
                 float* hi = chunk + (size_t)kb * mf::ST1_BYTES / 4;
                 float* lo = hi + mf::HC * 32;
+                const bool tail = packed && kb + 1 == pl.nkb1;      // one image: [hi(16 k) | lo(16 k)] per row
                 for (int r = 0; r < mf::HC; ++r) {
                     const int n = j * mf::HC + r;
                     if (n >= hidden) break;
-                    for (int kk = 0; kk < 32; ++kk) {
+                    for (int kk = 0; kk < (tail ? 16 : 32); ++kk) {
                         const int k = kb * 32 + kk;
                         if (k >= C) break;
-                        put_el(hi, lo, r, kk, W1.host[(size_t)n * C + k]);
+                        const float v = W1.host[(size_t)n * C + k];
+                        if (!tail) { put_el(hi, lo, r, kk, v); continue; }
+                        const float hv = tf32_rna(v);
+                        auto pos = [&](int col) { return (size_t)r * 32 + (size_t)(((col >> 2) ^ (r & 7)) << 2) + (col & 3); };
+                        hi[pos(kk)] = hv;
+                        hi[pos(16 + kk)] = tf32_rna(v - hv);
                     }
                 }
             }
+            const size_t fc1_floats = ((size_t)(pl.nkb1 - 1) * mf::ST1_BYTES + (packed ? mf::ST1T_BYTES : mf::ST1_BYTES)) / 4;
             for (int kb = 0; kb < 2; ++kb) {
-                float* hi = chunk + ((size_t)pl.nkb1 * mf::ST1_BYTES + (size_t)kb * pl.st2_bytes) / 4;
+                float* hi = chunk + fc1_floats + (size_t)kb * pl.st2_bytes / 4;
                 float* lo = hi + (size_t)pl.N2 * 32;
                 for (int r = 0; r < C; ++r)
                     for (int kk = 0; kk < 32; ++kk) {
@@ -727,26 +736,44 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
     const int B = c.B, W = c.W;
     const long long M = (long long)B * H * W;
     const float* src = x_in;
+    bool have_stats = false;      // wk.stats holds the LayerNorm statistics of `src` for the next consumer (written by the fused MLP)
     for (int j = 0; j < lw.depth; ++j) {
         const WindowGeom g = geom(H, W, (j & 1) ? 2 : 0);
         const long long nwin = (long long)B * g.nW, Mw = nwin * 16;
         const BlockW& bw = lw.blk[j];
-        if (c.L.tc && bw.qkvh.tc.img && C <= c.h->fuse_attn_max_c)
-            op_qkv_attn(c.L, bw, lw.heads, lw.hd, src, ld, g, Mw, c.wk.att, ld, (j & 1) != 0);
+        const bool fused_attn = c.L.tc && bw.qkvh.tc.img && C <= c.h->fuse_attn_max_c;
+        if (fused_attn)
+            op_qkv_attn(c.L, bw, lw.heads, lw.hd, src, ld, g, Mw, c.wk.att, ld, (j & 1) != 0, have_stats);
         else {
             op_qkv(c.L, bw, src, ld, g, Mw, c.wk.qkv, ldq);
             op_attention(c.L, c.wk.qkv, ldq, c.wk.att, ld, bw.relbias, lw.heads, lw.hd, lw.hdp, C, nwin, (j & 1) != 0, g);
         }
         op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
-        if (c.L.fuse_mlp && bw.mlpf.plan.ok) op_mlp_fused(c.L, bw, xw, ld, M, mf::StatsOut{});
-        else {
+        have_stats = false;
+        if (c.L.fuse_mlp && bw.mlpf.plan.ok) {
+            // the rows this kernel writes are the input of the next LayerNorm: let its epilogue emit their statistics
+            mf::StatsOut so{};
+            if (c.L.emit_stats) {
+                if (j + 1 < lw.depth) {
+                    const BlockW& nb = lw.blk[j + 1];
+                    if (c.L.tc && nb.qkvh.tc.img && C <= c.h->fuse_attn_max_c && qkv_attn_takes_stats(c.L, nb)) {
+                        so.out = c.wk.stats; so.geom = 1; so.H = H; so.W = W;
+                        so.ng = geom(H, W, ((j + 1) & 1) ? 2 : 0);
+                    }
+                } else if (lw.scale == 2) {
+                    so.out = c.wk.stats; so.geom = 0; so.H = H; so.W = W;       // PatchSplit normalises token rows
+                }
+            }
+            op_mlp_fused(c.L, bw, xw, ld, M, so);
+            have_stats = so.out != nullptr;
+        } else {
             op_mlp1(c.L, bw, xw, ld, M, c.wk.hid, ldh);
             op_mlp2(c.L, bw, c.wk.hid, ldh, M, xw, ld);
         }
         src = xw;
     }
     if (lw.scale == 1) op_merge(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim));
-    else if (lw.scale == 2) op_split(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim));
+    else if (lw.scale == 2) op_split(c.L, lw, xw, ld, B, H, W, out, ldc(lw.out_dim), have_stats);
 }
 
 // Encoder.forward (base.py:143-158) from the frame-major spectrum in wk.Sf.
@@ -860,6 +887,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.L.tc = h->use_tc;
     c.L.pvq_tc = h->use_tc && h->pvq_tc;
     c.L.fuse_mlp = h->use_tc && h->fuse_mlp;
+    c.L.emit_stats = h->emit_stats;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -930,6 +958,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
     if (const char* e = getenv("ESCB_FUSE_MLP")) h->fuse_mlp = atoi(e) != 0;
+    if (const char* e = getenv("ESCB_EMIT_STATS")) h->emit_stats = atoi(e) != 0;
     if (const char* e = getenv("ESCB_LN_POST")) h->ln_post = atoi(e);
     cudaGetDevice(&h->device);
     h->L = c.num_levels;

@@ -82,6 +82,7 @@ struct Launcher {                                    // stream + launch accounti
     cudaError_t err = cudaSuccess;
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
+    bool emit_stats = true;                          // the fused MLP emits the next LayerNorm's statistics (no pre-kernel for it)
     bool fuse_mlp = true;                            // LN2 -> fc1 -> GELU -> fc2 -> +x in one launch where a plan exists (ESCB_FUSE_MLP=0: the unfused pair)
     int ln_post = kLnPostDefault;                    // bit mask (ESCB_LN_POST): LayerNorm applied after the GEMM in 1 fused qkv+attention, 2 mlp1, 4 PatchSplit, 8 PatchMerge
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
@@ -137,7 +138,8 @@ void op_qkv(Launcher& L, const BlockW& w, const float* x, int ld, const WindowGe
 void op_attention(Launcher& L, const float* qkv, int ldq, float* att, int ldo, const float* relbias, int heads,
                   int hd, int hdp, int C, long long nwin, bool masked, const WindowGeom& g);
 void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x, int ld, const WindowGeom& g, long long M,
-                 float* att, int ldo, bool masked);
+                 float* att, int ldo, bool masked, bool stats_ready = false);
+bool qkv_attn_takes_stats(const Launcher& L, const BlockW& w);
 bool attention_fusable(int hd);
 void op_proj(Launcher& L, const BlockW& w, const float* att, int lda, const float* resid, float* y, int ld,
              const WindowGeom& g, long long M);
@@ -145,7 +147,7 @@ void op_mlp1(Launcher& L, const BlockW& w, const float* x, int ld, long long M, 
 void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long M, float* x, int ld);
 void op_mlp_fused(Launcher& L, const BlockW& w, float* x, int ld, long long M, const mf::StatsOut& so);
 void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
-void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy);
+void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy, bool stats_ready = false);
 cudaError_t swin_init();
 cudaError_t frontend_init();
 

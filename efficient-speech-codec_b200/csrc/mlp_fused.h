@@ -38,13 +38,25 @@ namespace mf {
 
 constexpr int BM = 128;
 constexpr int HC = 64;                  // hidden columns per chunk = UMMA N of fc1 = two K blocks of fc2
-constexpr int W_XLOAD = 0, W_WLOAD = 1, W_MMA = 2, W_ALLOC = 3;
-constexpr int LN_BASE = 4, GELU_BASE = 8, GELU_WARPS = 8, OUT_BASE = 16;
-constexpr int WARPS = 20, THREADS = WARPS * 32;
+// Warp ids: the schedulers favour high warp ids (measured in round 1 on the GEMM engine), and the single MMA-issuing
+// warp must not starve behind the ALU-heavy GELU warps that share its scheduler - it sits on top.
+#ifndef ESCB_MF_GELU_WARPS
+#define ESCB_MF_GELU_WARPS 8
+#endif
+constexpr int LN_BASE = 0, OUT_BASE = 4, GELU_BASE = 8, GELU_WARPS = ESCB_MF_GELU_WARPS;   // 8 or 16: 32 or 16 hidden columns per thread and chunk
+constexpr int GELU_COLS = HC / (GELU_WARPS / 4);
+constexpr int W_XLOAD = GELU_BASE + GELU_WARPS, W_WLOAD = W_XLOAD + 1, W_ALLOC = W_XLOAD + 2, W_MMA = W_XLOAD + 3;
+constexpr int WARPS = W_MMA + 1, THREADS = WARPS * 32;
 constexpr int MAX_WST = 16;             // weight stage barriers (ring slots, or all stages of a tile when resident)
 constexpr int MAX_NX = 3;
 constexpr int BOX_BYTES = BM * 128;     // one 32-column box of the x tile: 128 rows x 128 bytes
 constexpr int ST1_BYTES = 2 * HC * 128; // fc1 stage: [hi | lo] images of 64 hidden rows x one 32-wide K block
+// When the last K block of fc1 holds at most two k-steps (16 input channels: C = 45 -> k = 32..47, C = 72 -> k = 64..71)
+// its hi and lo values share ONE image: row r = [hi(k0..k0+15) | lo(k0..k0+15)], so the lo operand of k-step ks is the hi
+// descriptor advanced by 64 bytes.  Saves 8 KB per chunk: the third x slot at C = 45, 17 % of the fc1 stream at C = 72.
+constexpr int ST1T_BYTES = HC * 128;
+inline int fc1_tail_ksteps(int C) { return ((C + 7) / 8) % 4; }          // k-steps in the last K block (0: it is full)
+inline bool fc1_tail_packed(int C) { const int t = fc1_tail_ksteps(C); return t == 1 || t == 2; }
 constexpr int MAX_C = 96;
 
 // barrier indices
@@ -64,7 +76,7 @@ struct Plan {                       // geometry of the fused kernel for one chan
 
 inline Plan make_plan(int C, int hidden) {
     Plan pl;
-    if (C > MAX_C || hidden != 4 * C || (C > 48 && (C & 3))) return pl;
+    if ((C != 45 && C != 72 && C != 96) || hidden != 4 * C) return pl;      // widths the kernel is instantiated for (mlp_fused.cu)
     pl.C = C;
     pl.ld = (C + 3) & ~3;
     pl.Kp16 = (C + 15) & ~15;
@@ -76,7 +88,7 @@ inline Plan make_plan(int C, int hidden) {
     pl.rem = pl.ld % 32;
     pl.st2_bytes = (unsigned)pl.N2 * 256u;
     pl.slot_bytes = pl.st2_bytes > (unsigned)ST1_BYTES ? pl.st2_bytes : (unsigned)ST1_BYTES;
-    pl.chunk_bytes = (unsigned)pl.nkb1 * ST1_BYTES + 2u * pl.st2_bytes;
+    pl.chunk_bytes = (unsigned)(pl.nkb1 - 1) * ST1_BYTES + (fc1_tail_packed(C) ? ST1T_BYTES : ST1_BYTES) + 2u * pl.st2_bytes;
     pl.xslot_bytes = (unsigned)((pl.nboxf * BOX_BYTES + BM * pl.rem * 4 + 1023) & ~1023);
     pl.img_floats = (size_t)pl.nch * pl.chunk_bytes / 4;
     // TMEM: A1 buffers | R0 R1 | L buffers | ACC2 buffers
@@ -131,7 +143,8 @@ struct Weights {                    // device pointers of one block's fused-MLP 
 struct StatsOut { float2* out = nullptr; int geom = 0; int H = 0, W = 0; WindowGeom ng; };
 
 // mlp_fused.cu
-cudaError_t launch(cudaStream_t st, const Weights& w, float* x, long long M, float eps, const StatsOut& so);
+cudaError_t launch(cudaStream_t st, const Weights& w, float* x, long long M, float eps, const StatsOut& so,
+                   unsigned long long* trace = nullptr);
 
 }  // namespace mf
 }  // namespace escb

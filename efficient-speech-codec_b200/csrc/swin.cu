@@ -33,8 +33,12 @@ bool attention_fusable(int hd) {
     }
 }
 
+// The fused kernel can take LayerNorm statistics written by the producer of x (window-row indexed, mlp_fused.cu) when it
+// normalises in its A producers: the post-GEMM form reads the statistics of padded rows too, which no producer writes.
+bool qkv_attn_takes_stats(const Launcher& L, const BlockW& w) { return !((L.ln_post & 1) && w.qkvh_p.tc.img); }
+
 void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x, int ld, const WindowGeom& g, long long M,
-                 float* att, int ldo, bool masked) {
+                 float* att, int ldo, bool masked, bool stats_ready) {
     const int C = w.qkvh.K;
     L.begin(OP_QKV_ATTN, 2.0 * M * 3.0 * C * C + 64.0 * M * C, 4.0 * 2.0 * M * C);    // qkv + (q k^T, p v) ; x in, attention out
     const float scale = (float)(1.0 / sqrt((double)hd));
@@ -49,13 +53,13 @@ void op_qkv_attn(Launcher& L, const BlockW& w, int heads, int hd, const float* x
             ep.bias = w.qkvh_p.bias;                                                                                \
             e = tc::launch<false, AWindow, EP, 0, true>(L.st, al, lnpost(L, w.qkvh_p), w.qkvh_p, M, ep);        \
         } else                                                                                                      \
-            e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep);                               \
+            e = tc::launch<true, AWindow, EP>(L.st, al, lnp(L, w.n1), w.qkvh, M, ep, stats_ready);                  \
     } break;
         ESCB_FUSED_HDS(X)
 #undef X
         default: break;
     }
-    ++L.launches;          // the LayerNorm statistics pre-kernel
+    if (!stats_ready) ++L.launches;          // the LayerNorm statistics pre-kernel
     L.note(e);
 }
 
@@ -91,7 +95,7 @@ void op_mlp2(Launcher& L, const BlockW& w, const float* hid, int ldh, long long 
 void op_mlp_fused(Launcher& L, const BlockW& w, float* x, int ld, long long M, const mf::StatsOut& so) {
     const double C = w.fc1.K, Hd = w.fc1.N;
     L.begin(OP_MLP_FUSED, 4.0 * M * C * Hd, 4.0 * 2.0 * M * C);          // both GEMMs; x in, x out
-    cudaError_t e = ld == w.mlpf.plan.ld ? mf::launch(L.st, w.mlpf, x, M, kLnEps, so) : cudaErrorInvalidValue;
+    cudaError_t e = ld == w.mlpf.plan.ld ? mf::launch(L.st, w.mlpf, x, M, kLnEps, so, L.next_trace()) : cudaErrorInvalidValue;
     L.note(e);
 }
 
@@ -106,14 +110,15 @@ void op_merge(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H
     else L.note(GemmLauncher<true, AMerge, EpiRows<false, false>, 5, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 
-void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy) {
+void op_split(Launcher& L, const LayerW& w, const float* x, int ld, int B, int H, int W, float* y, int ldy, bool stats_ready) {
     ARows al{x, ld};
     EpiSplit ep{y, ldy, H, W, w.out_dim};
     const long long M = (long long)B * H * W;
     L.begin(OP_SPLIT, 2.0 * M * w.sub.N * w.sub.K, 4.0 * M * (w.sub.K + w.sub.N));
+    if (L.tc && !stats_ready) ++L.launches;       // the LayerNorm statistics pre-kernel
     if (L.tc && (L.ln_post & 4) && w.sub_p.tc.img)
-        ++L.launches, L.note(tc::launch<false, ARows, EpiSplit, kSplitWide, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep));
-    else if (L.tc) ++L.launches, L.note(tc::launch<true, ARows, EpiSplit, kSplitWide>(L.st, al, lnp(L, w.sn), w.sub, M, ep));
+        L.note(tc::launch<false, ARows, EpiSplit, kSplitWide, true>(L.st, al, lnpost(L, w.sub_p), w.sub_p, M, ep, stats_ready));
+    else if (L.tc) L.note(tc::launch<true, ARows, EpiSplit, kSplitWide>(L.st, al, lnp(L, w.sn), w.sub, M, ep, stats_ready));
     else L.note(GemmLauncher<true, ARows, EpiSplit, 6, 8, 9>::launch(L.st, al, lnp(L, w.sn), w.sub, M, ep));
 }
 

@@ -971,8 +971,11 @@ inline const TcWeight& pick(const GemmWeight& gw, long long M) {
 
 // LNP: the LayerNorm is applied after the GEMM (gw must hold the gamma-scaled image, ln.cs / ln.bw its vectors); the
 // producers then run the plain path (raw loads, no statistics / gamma / beta traffic, no normalisation arithmetic).
+// stats_ready: ln.stats already holds (mean, rstd) of every valid logical row (written by the producer of the input map,
+// e.g. the fused MLP kernel's epilogue): the statistics pre-kernel is skipped.
 template <bool LN, class AL, class EP, int WIDE = 0, bool LNP = false>
-inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep) {
+inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, const GemmWeight& gw, long long M, const EP& ep,
+                          bool stats_ready = false) {
     static_assert(!(LN && LNP), "LayerNorm is applied either in the producers or after the GEMM");
     const TcWeight& w = pick(gw, M);
     if (!w.img || M <= 0) return M <= 0 ? cudaSuccess : cudaErrorInvalidValue;
@@ -982,8 +985,10 @@ inline cudaError_t launch(cudaStream_t st, const AL& al, const LnParams& ln, con
     if (LNP && (!ln.cs || !ln.bw)) return cudaErrorInvalidValue;
     if (LN || LNP) {
         if (!ln.stats) return cudaErrorInvalidValue;
-        const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
-        if (e != cudaSuccess) return e;
+        if (!stats_ready) {
+            const cudaError_t e = launch_ln_stats(st, al, M, w.K, ln.eps, ln.stats);
+            if (e != cudaSuccess) return e;
+        }
     }
     return launch_e<LN, AL, EP, E, LNP>(st, al, ln, w, M, ep);
 }

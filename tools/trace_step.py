@@ -44,6 +44,14 @@ for phase in ("encode", "decode"):
           f"mma: wait_a_full% wait_acc_empty% wait_b_full% issue% | prod tile-init%")
     for i in range(1024):
         n = t[i, 13]
+        sig = int(buf.reshape(1024, 16)[i, 15])
+        if sig >> 60 == 0xF:        # fused MLP kernel (mlp_fused.cu)
+            C_, ntl, ctas = sig & 0xFFFFF, (sig >> 20) & 0xFFFFFFFF, max(t[i, 14], 1)
+            pct = lambda k, tot: 100 * t[i, k] / max(t[i, tot], 1)
+            print(f"{i:3d} MLP-FUSED C={C_:3d} | {ntl:5d} {int(ctas):3d} | {t[i,0]/ctas/1e3:7.1f} | mma wait: a1_full {pct(1,0):3.0f} h_full {pct(2,0):3.0f} "
+                  f"acc_free {pct(3,0):3.0f} w_full {pct(4,0):3.0f} | ln wait: x_full {pct(6,5):3.0f} a1_free {pct(7,5):3.0f} | "
+                  f"gelu wait: r_full {pct(9,8):3.0f} l_free {pct(10,8):3.0f} | out wait: acc_full {pct(12,11):3.0f}")
+            continue
         if n == 0:
             continue
         sig = int(buf.reshape(1024, 16)[i, 15])
