@@ -69,6 +69,7 @@ struct escb_handle {
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
     bool pvq_tc = true;        // ESCB_PVQ=simt keeps the product-VQ projections on the SIMT engine
     int ln_post = kLnPostDefault;   // ESCB_LN_POST bit mask (internal.h)
+    bool fuse_pvq = true;      // ESCB_FUSE_PVQ=0: three launches per RVQ stream step (down GEMM, argmin, up GEMM)
     bool emit_stats = true;    // ESCB_EMIT_STATS=0: every LayerNorm GEMM runs its own statistics pre-kernel (A/B debugging)
     bool fuse_mlp = true;      // ESCB_FUSE_MLP=0 keeps the unfused mlp1 + mlp2 pair everywhere (A/B debugging, variant tests)
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
@@ -796,14 +797,20 @@ static void pvq_encode(Ctx& c, int q, const float* enc, const float* dec, long l
 static void run_csrvq_encode(Ctx& c, int S, long long* codes) {
     escb_handle* h = c.h;
     const int L = h->L;
-    pvq_encode(c, 0, c.wk.enc[L - 1], nullptr, codes, S, 0);
+    // one stream step: quantize enc - dec, and (unless it is the last transmitted stream) refine dec in place
+    auto step = [&](int q, const float* enc, float* dec_in, float* dec_out, bool refine) {
+        if (c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], enc, dec_in, c.B, c.W, codes, S, q, refine ? dec_out : nullptr, nullptr, 0))
+            return;
+        pvq_encode(c, q, enc, dec_in, codes, S, q);
+        if (refine) op_pvq_up(c.L, h->quants[q], codes, S, q, dec_in, c.B, c.W, dec_out);
+    };
+    step(0, c.wk.enc[L - 1], nullptr, c.wk.dec[L - 1], S > 1);
     if (S == 1) return;
-    op_pvq_up(c.L, h->quants[0], codes, S, 0, nullptr, c.B, c.W, c.wk.dec[L - 1]);
     for (int i = 0; i < S - 1; ++i) {
         const int lv = L - 1 - i;
-        pvq_encode(c, i + 1, c.wk.enc[lv], c.wk.dec[lv], codes, S, i + 1);
-        if (i + 2 == S) break;
-        op_pvq_up(c.L, h->quants[i + 1], codes, S, i + 1, c.wk.dec[lv], c.B, c.W, c.wk.dec[lv]);
+        const bool last = i + 2 == S;
+        step(i + 1, c.wk.enc[lv], c.wk.dec[lv], c.wk.dec[lv], !last);
+        if (last) break;
         run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
     }
 }
@@ -822,10 +829,15 @@ static void run_backend(Ctx& c, float* audio, float* recon_feat) {
 static void run_csrvq_decode(Ctx& c, int S, const long long* codes) {
     escb_handle* h = c.h;
     const int L = h->L;
-    op_pvq_up(c.L, h->quants[0], codes, S, 0, nullptr, c.B, c.W, c.wk.dec[L - 1]);
+    auto up = [&](int q, const float* dec, float* out) {
+        if (c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], nullptr, dec, c.B, c.W, const_cast<long long*>(codes), S, q, out, nullptr, 0))
+            return;
+        op_pvq_up(c.L, h->quants[q], codes, S, q, dec, c.B, c.W, out);
+    };
+    up(0, nullptr, c.wk.dec[L - 1]);
     for (int i = 0; i < L - 1; ++i) {
         const int lv = L - 1 - i;
-        if (i < S - 1) op_pvq_up(c.L, h->quants[i + 1], codes, S, i + 1, c.wk.dec[lv], c.B, c.W, c.wk.dec[lv]);
+        if (i < S - 1) up(i + 1, c.wk.dec[lv], c.wk.dec[lv]);
         run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
     }
 }
@@ -836,6 +848,10 @@ static void run_csrvq_forward(Ctx& c, int S, long long* codes, float* loss) {
     const int L = h->L, T = c.W / 2;
     auto vq = [&](int q, const float* enc, const float* dec, float* out) {
         const QuantW& qw = h->quants[q];
+        if (c.L.fuse_pvq && op_pvq_stream(c.L, qw, enc, dec, c.B, c.W, codes, S, q, out, loss ? c.wk.ze : nullptr, ldc(3 * qw.d))) {
+            if (loss) op_vq_loss(c.L, qw, c.wk.ze, ldc(3 * qw.d), codes, S, q, c.B, T, loss);
+            return;
+        }
         pvq_encode(c, q, enc, dec, codes, S, q);
         if (loss) op_vq_loss(c.L, qw, c.wk.ze, ldc(3 * qw.d), codes, S, q, c.B, T, loss);
         op_pvq_up(c.L, qw, codes, S, q, dec, c.B, c.W, out);
@@ -888,6 +904,7 @@ static int begin(escb_handle* h, Ctx& c, int B, int W, int T, int what, void* ws
     c.L.pvq_tc = h->use_tc && h->pvq_tc;
     c.L.fuse_mlp = h->use_tc && h->fuse_mlp;
     c.L.emit_stats = h->emit_stats;
+    c.L.fuse_pvq = h->fuse_pvq;
     Bump dry(nullptr, 0);
     Work tmp;
     const size_t need = plan(h, B, W, T, what, dry, tmp);
@@ -959,6 +976,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
     if (const char* e = getenv("ESCB_FUSE_MLP")) h->fuse_mlp = atoi(e) != 0;
     if (const char* e = getenv("ESCB_EMIT_STATS")) h->emit_stats = atoi(e) != 0;
+    if (const char* e = getenv("ESCB_FUSE_PVQ")) h->fuse_pvq = atoi(e) != 0;
     if (const char* e = getenv("ESCB_LN_POST")) h->ln_post = atoi(e);
     cudaGetDevice(&h->device);
     h->L = c.num_levels;
@@ -978,6 +996,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (e == cudaSuccess) { *h->err_host = 0; e = cudaHostGetDevicePointer((void**)&h->err_dev, h->err_host, 0); }
     if (e == cudaSuccess) e = swin_init();
     if (e == cudaSuccess) e = frontend_init();
+    if (e == cudaSuccess) e = pvq_init();
     if (e != cudaSuccess) {
         delete h;
         return fail(ESCB_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(e));
@@ -1277,8 +1296,23 @@ int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes, const float
     if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
     Ctx c;
     if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
-    op_pvq_up(c.L, h->quants[q], (const long long*)codes, 1, 0, dec, B, W, out);
+    if (!(c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], nullptr, dec, B, W, (long long*)codes, 1, 0, out, nullptr, 0)))
+        op_pvq_up(c.L, h->quants[q], (const long long*)codes, 1, 0, dec, B, W, out);
     return finish(c, "escb_pvq_decode");
+}
+
+int escb_pvq_stream(escb_handle* h, int32_t q, const float* enc, const float* dec, int32_t B, int32_t W, int64_t* codes,
+                    float* out, void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!enc || !codes) return fail(ESCB_EINVAL, "null argument");
+    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    Ctx c;
+    if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
+    if (!(c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], enc, dec, B, W, (long long*)codes, 1, 0, out, nullptr, 0))) {
+        pvq_encode(c, q, enc, dec, (long long*)codes, 1, 0);
+        if (out) op_pvq_up(c.L, h->quants[q], (const long long*)codes, 1, 0, dec, B, W, out);
+    }
+    return finish(c, "escb_pvq_stream");
 }
 
 int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, int64_t rows, int64_t* idx, void* stream) {
@@ -1311,7 +1345,7 @@ int escb_code_histogram(const int64_t* codes, int32_t B, int32_t S, int32_t G, i
 static const char* const kOpNames[OP_COUNT] = {
     "stft_gemm", "patch_embed", "qkv_gemm", "window_attention", "proj_gemm", "mlp1_gemm", "mlp2_gemm", "merge_gemm",
     "split_gemm", "pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "vq_loss", "deembed_conv5x5_gemm",
-    "deembed_conv3x3", "istft_gemm", "layout", "qkv_attention_fused", "mlp_fused"};
+    "deembed_conv3x3", "istft_gemm", "layout", "qkv_attention_fused", "mlp_fused", "pvq_stream_fused"};
 
 int escb_profile_begin(escb_handle* h) {
     if (!h) return fail(ESCB_EINVAL, "null handle");

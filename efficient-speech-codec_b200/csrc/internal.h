@@ -65,7 +65,7 @@ struct FrontW {
 // Kernel classes for launch accounting / per-op timing (escb_profile_begin/end).
 enum OpId {
     OP_STFT, OP_EMBED, OP_QKV, OP_ATTN, OP_PROJ, OP_MLP1, OP_MLP2, OP_MERGE, OP_SPLIT, OP_PVQ_DOWN, OP_ARGMIN,
-    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_QKV_ATTN, OP_MLP_FUSED, OP_COUNT
+    OP_PVQ_UP, OP_VQLOSS, OP_DEEMBED1, OP_DEEMBED2, OP_ISTFT, OP_LAYOUT, OP_QKV_ATTN, OP_MLP_FUSED, OP_PVQ_STREAM, OP_COUNT
 };
 static_assert(OP_COUNT == ESCB_NUM_OPS, "escb200.h ESCB_NUM_OPS out of date");
 
@@ -83,6 +83,7 @@ struct Launcher {                                    // stream + launch accounti
     bool tc = true;                                  // dense layers on the tcgen05 engine (false: fp32 SIMT engine)
     bool pvq_tc = true;                              // product-VQ projections on the tcgen05 engine
     bool emit_stats = true;                          // the fused MLP emits the next LayerNorm's statistics (no pre-kernel for it)
+    bool fuse_pvq = true;                            // one launch per RVQ stream step (ESCB_FUSE_PVQ=0: down GEMM + argmin + up GEMM)
     bool fuse_mlp = true;                            // LN2 -> fc1 -> GELU -> fc2 -> +x in one launch where a plan exists (ESCB_FUSE_MLP=0: the unfused pair)
     int ln_post = kLnPostDefault;                    // bit mask (ESCB_LN_POST): LayerNorm applied after the GEMM in 1 fused qkv+attention, 2 mlp1, 4 PatchSplit, 8 PatchMerge
     Profiler* prof = nullptr;                        // non-null: bracket every launch with CUDA events
@@ -158,6 +159,10 @@ void op_argmin(Launcher& L, const QuantW& q, int g_first, int groups, const floa
 void op_pvq_up(Launcher& L, const QuantW& q, const long long* codes, int S, int s, const float* dec, int B, int W,
                float* out);
 void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G, int T, int ncodes, float* counts);
+// fused stream step (kernels.cuh pvq_stream_kernel); returns false when this quantizer's geometry has no fused kernel
+bool op_pvq_stream(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, long long* codes, int S,
+                   int s, float* out, float* ze, int ldz);
+cudaError_t pvq_init();
 void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
                 int T, float* loss);
 

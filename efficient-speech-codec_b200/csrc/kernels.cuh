@@ -449,4 +449,306 @@ code_histogram_kernel(const long long* __restrict__ codes, const int B, const in
     for (int i = threadIdx.x; i < ncodes; i += blockDim.x) out[i] += (float)hist[i];
 }
 
+// ------------------------------------------------------------------------------------------------ fused RVQ stream step
+// One cross-scale RVQ stream step in ONE launch (csrvq.py:23-60 + quantization.py:74-136 + codebook.py:20-55):
+//   residual = enc - dec (pre_process gather) -> per-group down-projection -> L2-normalise -> distance to the 1024
+//   normalised codewords, first minimum -> code -> raw codeword -> up-projection -> post_process scatter (+ dec).
+// The three product-VQ groups are independent (own projection, own codebook, disjoint (o, c) thirds of the frame), so a
+// CTA is (tile of FR VQ frames) x (one group): N = 1024 frames give 384 CTAs.  The residual third lives in shared memory
+// (FR x K_g floats, row pitch K_g + 4), z / z_hat / the chosen codewords in a few hundred bytes; enc and dec are read
+// once (dec a second time, from L2, for the final add) and the refined map is written once: the step is HBM-bound
+// (8.6 flop/B over the six streams of ESC-Base).
+// Arithmetic is that of the unfused kernels, operation for operation: every down-projection output is ONE sequential
+// k = 0..K_g-1 FMA chain (gemm_tile's order), the normalisation and the distance (|z|^2 - (2z).c) + |c|^2 follow
+// codebook_argmin_kernel, and ties go to the lowest index.  The distance loop runs two codes per FFMA2.
+// Requires the groups to be equal thirds of every frequency run (QuantW::run > 0) and ld == C.
+struct PvqStreamArgs {
+    const float* E;             // encoder map of the scale   [B, Hq*W, C]
+    const float* Dm;            // decoder state (null: stream 0 quantizes enc itself)
+    float* out;                 // dec_refine = vq.decode(code) + dec (null: codes only; may alias Dm)
+    long long* codes;           // [B, S, 3, T] (this stream's slice: + s*3*T)
+    long long cstride;          // batch stride of codes (S*3*T)
+    float* ze;                  // optional [rows][ldz] projected vectors (the eval-mode VQ loss reads them)
+    int ldz;
+    const float* wd[3];         // per group Wt [Kg_pad][ldwd]
+    int ldwd;
+    const float* wu;            // up-projection Wt [3d][ldwu], rows g*d + j, columns in frame order (h, o, c)
+    int ldwu;
+    const float* cbt;           // [3][d][ncodes] normalised, transposed
+    const float* cnorm;         // [3][ncodes]
+    const float* raw;           // [3][ncodes][d]
+    int* bad;                   // host-mapped latch for out-of-range codes given to the decode-only form
+    int ncodes, Hq, W, C, run, Kg, T;
+    long long rows;             // B * T
+    FastDiv drun4;              // by run / 4 (float4 groups per frequency run)
+    int lgH;                    // log2(Hq) when Hq is a power of two, else -1
+    int decode_only;            // codes are given (ProductVectorQuantize.decode + post_fuse): steps 5 and 6 only
+};
+constexpr int kPvqKC = 64;      // k rows of the down-projection staged in shared memory per chunk
+constexpr int kPvqStages = 4;   // chunks in flight (cp.async ring): one chunk is 0.25 us of FMA chain, an L2 / DRAM round trip 0.5 - 1.5 us
+
+template <int D, int FR>
+__global__ void __launch_bounds__(256, 3)
+pvq_stream_kernel(const PvqStreamArgs a) {
+    constexpr int LDW = (D + 3) & ~3;                           // row pitch of the packed down-projection Wt [k][LDW]
+    constexpr int WL4 = (kPvqKC * LDW / 4 + 255) / 256;         // float4 loads per thread and weight chunk
+    constexpr int SUB = FR < 8 ? FR : 8;                        // frames per pass of the distance loop (register tile)
+    extern __shared__ __align__(16) float rs[];                 // [FR][Kg + 4], then the weight ring [kPvqStages][kPvqKC][LDW]
+    __shared__ __align__(16) float zs[FR][D];                   // z
+    __shared__ __align__(16) unsigned long long z2s[FR][D];     // (2 z_hat, 2 z_hat) pairs: the FFMA2 operand of the distance loop
+    __shared__ float zzs[FR];
+    __shared__ __align__(16) float es[FR][D];                   // chosen raw codewords
+    __shared__ float redv[FR][8];
+    __shared__ int redi[FR][8];
+    __shared__ int best_code[FR];
+    __shared__ long long fbase[FR];                             // element offset of (frame, h = 0) + this group's third
+    const int tid = threadIdx.x, g = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * FR;
+    const int Kg = a.Kg, pitch = Kg + 4, run = a.run, goff = g * run;
+    const int nval = a.rows - row0 >= FR ? FR : (int)(a.rows - row0);
+    const long long hstride = (long long)a.W * a.C;
+    if (tid < FR) {
+        const long long m = row0 + (tid < nval ? tid : 0), b = m / a.T;
+        const int t = (int)(m - b * a.T);
+        fbase[tid] = ((long long)b * a.Hq * a.W + 2 * t) * a.C + goff;
+        if (a.decode_only) {
+            int code = 0;
+            if (tid < nval) {
+                const long long cv = a.codes[b * a.cstride + (long long)g * a.T + t];
+                code = (cv < 0 || cv >= a.ncodes) ? 0 : (int)cv;
+                if (cv != code && a.bad) *(volatile int*)a.bad = 1;      // caller data: clamp and latch (escb_poll_error)
+            }
+            best_code[tid] = code;
+        }
+    }
+    __syncthreads();
+    if (!a.decode_only) {
+        // ---- 1. residual third of FR frames -> shared memory (runs of `run` contiguous floats per frequency row).
+        // Item = one float4 of one (frame, frequency row) run; four items per thread are loaded before any is consumed.
+        {
+            const int run4 = run >> 2, nitem = FR * a.Hq * run4;
+            auto locate = [&](int idx, int& f, int& k, long long& goffs) {   // item -> frame, k, offset inside the frame
+                const int row = (int)a.drun4.div((unsigned)idx), x4 = idx - row * run4;
+                int h;
+                if (a.lgH >= 0) { f = row >> a.lgH; h = row & (a.Hq - 1); }
+                else { f = row / a.Hq; h = row - f * a.Hq; }
+                k = h * run + 4 * x4;
+                goffs = h * hstride + 4 * x4;
+            };
+            for (int base = tid; base < nitem; base += 4 * 256) {
+                float4 e[4], d[4];
+                int f[4], k[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + 256 * u;
+                    e[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    d[u] = e[u];
+                    f[u] = -1;
+                    if (idx < nitem) {
+                        long long goffs;
+                        locate(idx, f[u], k[u], goffs);
+                        if (f[u] < nval) {
+                            const long long off = fbase[f[u]] + goffs;
+                            e[u] = ldg4(a.E + off);
+                            if (a.Dm) d[u] = ldg4(a.Dm + off);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (f[u] >= 0)
+                        *reinterpret_cast<float4*>(rs + f[u] * pitch + k[u]) =
+                            make_float4(e[u].x - d[u].x, e[u].y - d[u].y, e[u].z - d[u].z, e[u].w - d[u].w);
+            }
+        }
+        // ---- 2. down-projection: one sequential FMA chain per (frame, component), the order of gemm_tile.  The weight
+        // streams through a cp.async ring of kPvqKC-row chunks in shared memory (all 256 threads copy).
+        {
+            float* wsm = rs + FR * pitch;
+            const float* wg = a.wd[g];
+            // thread = (group of PF frames, component j): PF independent chains share every weight read, and the residual
+            // is read four k at a time (1.5 instructions per multiply-add instead of 3; the chains fill the FMA latency)
+            constexpr int PF = 4;
+            static_assert(FR % PF == 0, "frames per CTA must be a multiple of 4");
+            const bool active = tid < (FR / PF) * D;
+            const int fg = active ? tid / D : 0, oj = active ? tid - (tid / D) * D : 0;
+            float acc[PF];
+#pragma unroll
+            for (int i = 0; i < PF; ++i) acc[i] = 0.f;
+            const int nchunks = Kg / kPvqKC;
+            auto issue = [&](int ch) {                         // chunk ch -> ring slot ch % kPvqStages (16-byte cp.async, all threads)
+                if (ch < nchunks) {
+                    const float* src = wg + (long long)ch * kPvqKC * LDW;
+                    float* dst = wsm + (ch % kPvqStages) * kPvqKC * LDW;
+#pragma unroll
+                    for (int i = 0; i < WL4; ++i) {
+                        const int idx = tid + 256 * i;
+                        if (idx < kPvqKC * LDW / 4)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + 4 * idx)), "l"(src + 4 * idx) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+#pragma unroll
+            for (int st = 0; st < kPvqStages - 1; ++st) issue(st);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kPvqStages - 2) : "memory");
+                __syncthreads();                               // chunk ch has landed for everyone; slot (ch - 1) % stages is free
+                issue(ch + kPvqStages - 1);
+                const float* wc = wsm + (ch % kPvqStages) * kPvqKC * LDW + oj;
+                if (active) {
+                    const float* r = rs + (fg * PF) * pitch + ch * kPvqKC;
+#pragma unroll 4
+                    for (int kk = 0; kk < kPvqKC; kk += 4) {
+                        float4 rv[PF];
+#pragma unroll
+                        for (int i = 0; i < PF; ++i) rv[i] = *reinterpret_cast<const float4*>(r + i * pitch + kk);
+                        const float w0 = wc[kk * LDW], w1 = wc[(kk + 1) * LDW], w2 = wc[(kk + 2) * LDW], w3 = wc[(kk + 3) * LDW];
+#pragma unroll
+                        for (int i = 0; i < PF; ++i) {
+                            acc[i] = fmaf(rv[i].x, w0, acc[i]);
+                            acc[i] = fmaf(rv[i].y, w1, acc[i]);
+                            acc[i] = fmaf(rv[i].z, w2, acc[i]);
+                            acc[i] = fmaf(rv[i].w, w3, acc[i]);
+                        }
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    const int f = fg * PF + i;
+                    zs[f][oj] = acc[i];
+                    if (a.ze && f < nval) a.ze[(row0 + f) * (long long)a.ldz + g * D + oj] = acc[i];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. L2 normalisation (codebook.py:32-33), one thread per frame
+        if (tid < FR) {
+            float zn[D];
+            float ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { zn[k] = zs[tid][k]; ss = fmaf(zn[k], zn[k], ss); }
+            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+            float zz = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float v = zn[k] / denom;
+                zz = fmaf(v, v, zz);
+                z2s[tid][k] = pack2(2.0f * v, 2.0f * v);
+            }
+            zzs[tid] = zz;
+        }
+        __syncthreads();
+        // ---- 4. distances to all codewords: 4 codes per thread, SUB frames per pass, two codes per FFMA2
+        const float* cb = a.cbt + (long long)g * D * a.ncodes;
+        const float* cn = a.cnorm + (long long)g * a.ncodes;
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int f0 = 0; f0 < FR; f0 += SUB) {
+            float best[SUB];
+            int besti[SUB];
+#pragma unroll
+            for (int f = 0; f < SUB; ++f) { best[f] = 3.0e38f; besti[f] = 0x7fffffff; }
+            for (int c0 = tid * 4; c0 < a.ncodes; c0 += 1024) {
+                unsigned long long acc[SUB][2];
+#pragma unroll
+                for (int f = 0; f < SUB; ++f) { acc[f][0] = 0ull; acc[f][1] = 0ull; }
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb + (long long)k * a.ncodes + c0));
+                    const unsigned long long c01 = pack2(c4.x, c4.y), c23 = pack2(c4.z, c4.w);
+#pragma unroll
+                    for (int f = 0; f < SUB; ++f) {
+                        const unsigned long long z2 = z2s[f0 + f][k];
+                        acc[f][0] = ffma2(z2, c01, acc[f][0]);
+                        acc[f][1] = ffma2(z2, c23, acc[f][1]);
+                    }
+                }
+                const float4 cn4 = __ldg(reinterpret_cast<const float4*>(cn + c0));
+                const float cnj[4] = {cn4.x, cn4.y, cn4.z, cn4.w};
+#pragma unroll
+                for (int f = 0; f < SUB; ++f) {
+                    float d4[4];
+                    unpack2(acc[f][0], d4[0], d4[1]);
+                    unpack2(acc[f][1], d4[2], d4[3]);
+                    const float zz = zzs[f0 + f];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float dist = (zz - d4[j]) + cnj[j];
+                        if (dist < best[f]) { best[f] = dist; besti[f] = c0 + j; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < SUB; ++f) {
+                float bv = best[f];
+                int bi = besti[f];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) { redv[f0 + f][wid] = bv; redi[f0 + f][wid] = bi; }
+            }
+        }
+        __syncthreads();
+        if (tid < FR) {
+            float bv = redv[tid][0];
+            int bi = redi[tid][0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) {
+                const float ov = redv[tid][w];
+                const int oi = redi[tid][w];
+                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (bi == 0x7fffffff) bi = 0;                       // all-NaN row
+            best_code[tid] = bi;
+            if (tid < nval) {
+                const long long m = row0 + tid, b = m / a.T;
+                const int t = (int)(m - b * a.T);
+                a.codes[b * a.cstride + (long long)g * a.T + t] = bi;
+            }
+        }
+        if (!a.out) return;
+        __syncthreads();
+    }
+    // ---- 5. de-quantise from the RAW table (codebook.py:45-55)
+    for (int o = tid; o < FR * D; o += 256) {
+        const int f = o / D, j = o - f * D;
+        es[f][j] = __ldg(a.raw + ((long long)g * a.ncodes + best_code[f]) * D + j);
+    }
+    __syncthreads();
+    // ---- 6. up-projection + post_process scatter + post_fuse: thread = column of this group's third
+    for (int kg = tid; kg < Kg; kg += 256) {
+        const int h = kg / run, x = kg - h * run;
+        const float* u = a.wu + (long long)(g * D) * a.ldwu + (long long)h * 2 * a.C + goff + x;
+        float uj[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) uj[j] = __ldg(u + (long long)j * a.ldwu);
+        const long long col = h * hstride + x;
+#pragma unroll 2
+        for (int f = 0; f < nval; ++f) {
+            float acc = 0.f;
+            if constexpr (D % 4 == 0) {
+#pragma unroll
+                for (int j = 0; j < D; j += 4) {
+                    const float4 e4 = *reinterpret_cast<const float4*>(&es[f][j]);
+                    acc = fmaf(e4.x, uj[j], acc); acc = fmaf(e4.y, uj[j + 1], acc);
+                    acc = fmaf(e4.z, uj[j + 2], acc); acc = fmaf(e4.w, uj[j + 3], acc);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < D; j += 2) {
+                    const float2 e2 = *reinterpret_cast<const float2*>(&es[f][j]);
+                    acc = fmaf(e2.x, uj[j], acc); acc = fmaf(e2.y, uj[j + 1], acc);
+                }
+            }
+            const long long off = fbase[f] + col;
+            a.out[off] = a.Dm ? acc + a.Dm[off] : acc;
+        }
+    }
+}
+
 }  // namespace escb

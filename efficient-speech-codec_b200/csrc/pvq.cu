@@ -74,6 +74,77 @@ void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const lo
     L.note(cudaGetLastError());
 }
 
+template <int D, int FR>
+static cudaError_t launch_stream(cudaStream_t st, const PvqStreamArgs& a) {
+    constexpr int LDW = (D + 3) & ~3;
+    const size_t smem = a.decode_only ? 0 : ((size_t)FR * (a.Kg + 4) + kPvqStages * kPvqKC * LDW) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((a.rows + FR - 1) / FR), 3);
+    pvq_stream_kernel<D, FR><<<grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <int D>
+static cudaError_t launch_stream_d(cudaStream_t st, const PvqStreamArgs& a) {
+    // Frames per CTA: 8 while that is what fills the GPU (N = 1024 frames -> 384 CTAs); with more rows 16 or 32 - every CTA
+    // streams its group's projections and codebook from L2, so more frames per CTA means fewer bytes per frame - bounded by
+    // two co-resident CTAs (~100 KB of residual tile each).
+    const long long ctas8 = (a.rows + 7) / 8 * 3;
+    if (ctas8 < 4 * 148) return launch_stream<D, 8>(st, a);
+    if (ctas8 >= 16 * 148 && (a.decode_only || (size_t)32 * (a.Kg + 4) * sizeof(float) <= 100 * 1024)) return launch_stream<D, 32>(st, a);
+    if (a.decode_only || (size_t)16 * (a.Kg + 4) * sizeof(float) <= 100 * 1024) return launch_stream<D, 16>(st, a);
+    return launch_stream<D, 8>(st, a);
+}
+#define ESCB_STREAM_DS(X) X(6) X(8) X(12) X(16) X(24) X(32)
+
+cudaError_t pvq_init() {
+    cudaError_t e = cudaSuccess;
+#define X(n)                                                                                                                        \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pvq_stream_kernel<n, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pvq_stream_kernel<n, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pvq_stream_kernel<n, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    ESCB_STREAM_DS(X)
+#undef X
+    return e;
+}
+
+// enc == nullptr: decode-only form (codes are read, out = vq.decode(codes) + dec) with the fused kernel's up-projection
+// arithmetic, so that decode(encode(x)) reproduces forward(x) bit for bit like the reference does.
+bool op_pvq_stream(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, long long* codes, int S,
+                   int s, float* out, float* ze, int ldz) {
+    if (q.run <= 0 || (q.run & 3) || (q.ncodes & 3) || !argmin_supported(q.d) || (q.run * q.in_freq) % kPvqKC) return false;
+    if (!enc && !out) return false;
+    const int T = W / 2;
+    PvqStreamArgs a;
+    a.E = enc; a.Dm = dec; a.out = out;
+    a.codes = codes + (long long)s * 3 * T;
+    a.cstride = (long long)S * 3 * T;
+    a.ze = ze; a.ldz = ldz;
+    for (int g = 0; g < 3; ++g) a.wd[g] = q.down_g[g].wt;
+    a.ldwd = q.down_g[0].ldw;
+    a.wu = q.up.wt; a.ldwu = q.up.ldw;
+    a.cbt = q.cbt; a.cnorm = q.cnorm; a.raw = q.raw;
+    a.ncodes = q.ncodes; a.Hq = q.in_freq; a.W = W; a.C = q.in_dim; a.run = q.run; a.Kg = q.run * q.in_freq; a.T = T;
+    a.rows = (long long)B * T;
+    a.decode_only = enc ? 0 : 1;
+    a.drun4 = FastDiv::make((unsigned)(q.run / 4));
+    a.lgH = -1;
+    for (int l = 0; l < 16; ++l) if ((1 << l) == q.in_freq) a.lgH = l;
+    a.bad = L.code_err;
+    const double M = (double)a.rows, fd = q.frame_dim;
+    if (enc) L.begin(OP_PVQ_STREAM, 2.0 * M * (fd * q.d * (out ? 2.0 : 1.0) + 3.0 * q.ncodes * q.d),
+                     4.0 * M * fd * ((dec ? 2.0 : 1.0) + (out ? 1.0 : 0.0)) + 24.0 * M);
+    else L.begin(OP_PVQ_UP, 2.0 * M * fd * q.d, 4.0 * M * fd * (dec ? 2.0 : 1.0) + 24.0 * M);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (q.d) {
+#define X(n) case n: e = launch_stream_d<n>(L.st, a); break;
+        ESCB_STREAM_DS(X)
+#undef X
+        default: break;
+    }
+    L.note(e);
+    return true;
+}
+
 void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G, int T, int ncodes, float* counts) {
     L.begin(OP_LAYOUT, 0.0, 8.0 * B * S * G * T + 8.0 * S * G * ncodes);
     code_histogram_kernel<<<S * G, 256, (size_t)ncodes * sizeof(unsigned), L.st>>>(codes, B, S, G, T, ncodes, counts, L.code_err);

@@ -26,9 +26,9 @@ EXPORTS = [
     "escb_workspace_bytes", "escb_encode", "escb_decode", "escb_forward", "escb_encode_host", "escb_decode_host",
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
-    "escb_poll_error", "escb_code_histogram",
+    "escb_poll_error", "escb_code_histogram", "escb_pvq_stream",
 ]
-ESCB_NUM_OPS = 19
+ESCB_NUM_OPS = 20
 
 
 class NativeLibraryMissing(ImportError):
@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
         "escb_swin_layer": (C.c_int, [vp, i32, vp, i32, i32, i32, vp, vp, sz, vp]),
         "escb_pvq_encode": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, sz, vp]),
         "escb_pvq_decode": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, sz, vp]),
+        "escb_pvq_stream": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, vp, vp, sz, vp]),
         "escb_codebook_argmin": (C.c_int, [vp, i32, i32, vp, i64, vp, vp]),
         "escb_launch_count": (i64, [vp]),
         "escb_poll_error": (C.c_int, [vp]),

@@ -37,7 +37,7 @@ extern "C" {
 #define ESCB_ABI_VERSION 1
 #define ESCB_MAX_LEVELS 8
 #define ESCB_MAX_DEPTH 8
-#define ESCB_NUM_OPS 19
+#define ESCB_NUM_OPS 20
 
 enum {
     ESCB_OK = 0,
@@ -172,6 +172,12 @@ ESCB_API int escb_pvq_encode(escb_handle* h, int32_t q, const float* enc_dev, co
  * (dec_dev may be NULL).  out_dev [B, in_freq_q*W, in_dim_q]. */
 ESCB_API int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes_dev, const float* dec_dev, int32_t batch,
                     int32_t W, float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* One cross-scale RVQ stream step, CrossScaleRVQ.csrvq in eval mode (esc/models/csrvq.py:23-48 = csrvq_encode +
+ * csrvq_decode, :50-60): codes = vq.encode(enc - dec), out = vq.decode(codes) + dec, in ONE kernel launch.  dec_dev may be
+ * NULL (stream 0), out_dev may be NULL (codes only: the last transmitted stream of ESC.encode) and may alias dec_dev.
+ *   enc_dev/dec_dev/out_dev [B, in_freq_q*W, in_dim_q]; codes_dev [B, group_size, W/overlap] int64. */
+ESCB_API int escb_pvq_stream(escb_handle* h, int32_t q, const float* enc_dev, const float* dec_dev, int32_t batch, int32_t W,
+                    int64_t* codes_dev, float* out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Codebook.quantize_to_code (esc/modules/vq/codebook.py:20-43), THE RVQ argmin, for group `g` of stream `q`:
  *   z_dev [rows, codebook_dim_q] (already down-projected) -> idx_dev [rows] int64. */
 ESCB_API int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z_dev, int64_t rows, int64_t* idx_dev,

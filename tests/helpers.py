@@ -98,6 +98,18 @@ class Unit:
         n.check(self.lib.escb_pvq_decode(self.h.ptr, q, n.ptr(c), n.ptr(d), B, W, n.ptr(out), n.ptr(ws), ws.numel(), self._st()))
         return out.cpu()
 
+    def pvq_stream(self, q, enc, dec, W, refine=True):
+        """escb_pvq_stream: codes = vq.encode(enc - dec) and out = vq.decode(codes) + dec in one launch."""
+        t, n = self.torch, self.native
+        B = enc.shape[0]
+        e = enc.to(self.dev).contiguous()
+        d = None if dec is None else dec.to(self.dev).contiguous()
+        codes = t.empty((B, 3, W // 2), dtype=t.int64, device=self.dev)
+        out = t.empty_like(e) if refine else None
+        ws = self._ws(B, W)
+        n.check(self.lib.escb_pvq_stream(self.h.ptr, q, n.ptr(e), n.ptr(d), B, W, n.ptr(codes), n.ptr(out), n.ptr(ws), ws.numel(), self._st()))
+        return codes.cpu(), (None if out is None else out.cpu())
+
     def argmin(self, q, g, z):
         t, n = self.torch, self.native
         zz = z.to(self.dev).contiguous()

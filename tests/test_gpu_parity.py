@@ -194,6 +194,32 @@ def test_pvq_streams_config4_1024_frames(base6):
         assert maxabs(gotd, refd) <= 2e-6, q
 
 
+@pytest.mark.parametrize("W,B", [(12, 3), (2048, 1), (300, 5)])
+def test_pvq_fused_stream_step(base6, W, B):
+    """escb_pvq_stream (one launch per stream step: residual gather, down-projection, normalise, argmin, raw gather,
+    up-projection, scatter + dec) against the oracle's vq.encode / vq.decode: ragged tile counts, BASELINE configs[3]
+    size (1024 frames), and the unfused three-kernel path (ESCB_FUSE_PVQ=0 handle) as a second witness."""
+    from oracle.esc_oracle import pvq_decode, pvq_encode
+    m, o = base6
+    u = Unit(m)
+    c = o.cfg
+    for q in range(6):
+        g = torch.Generator().manual_seed(1000 * W + q)
+        C, Hq = c.quantizer_geometry(q)
+        enc = torch.randn(B, Hq * W, C, generator=g)
+        dec = None if q == 0 else torch.randn(B, Hq * W, C, generator=g)
+        resid = enc if dec is None else enc - dec
+        ref = pvq_encode(o.sd, f"quantizers.{q}", resid, Hq, c)
+        refd = pvq_decode(o.sd, f"quantizers.{q}", ref, Hq, c)
+        refd = refd if dec is None else refd + dec
+        codes, out = u.pvq_stream(q, enc, dec, W)
+        assert torch.equal(codes, ref), q
+        assert maxabs(out, refd) <= 2e-6, q
+        codes2, none = u.pvq_stream(q, enc, dec, W, refine=False)
+        assert none is None and torch.equal(codes2, ref)
+        assert torch.equal(u.pvq_encode(q, enc, dec, W), ref)            # the unfused kernels agree
+
+
 def test_codebook_argmin_bit_exact_and_ties(base6):
     """Codebook.quantize_to_code incl. rows that tie exactly: the lowest index must win."""
     from oracle.esc_oracle import codebook_argmin
@@ -255,7 +281,7 @@ def test_full_batch_properties(base0):
 
 
 @pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"},
-                                 {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}, {"ESCB_FUSE_MLP": "0"},
+                                 {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}, {"ESCB_FUSE_MLP": "0"}, {"ESCB_FUSE_PVQ": "0"}, {"ESCB_EMIT_STATS": "0"},
                                  {"ESCB_FUSE_MLP": "0", "ESCB_FUSE_ATTN_MAXC": "0"}])
 def test_engine_variants_agree(base0, env, monkeypatch):
     """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair, the fp32 SIMT engine, the fused
