@@ -64,6 +64,7 @@ struct escb_handle {
     float* arena = nullptr;
     LayerW layers[2 * ESCB_MAX_LEVELS];
     QuantW quants[ESCB_MAX_LEVELS];
+    RvqW rvq;                  // RVQCodecs only (cfg.num_rvqs > 0)
     FrontW front;
     std::atomic<long long> launches{0};
     bool use_tc = true;        // ESCB_GEMM=simt selects the fp32 SIMT engine for the dense layers (A/B debugging)
@@ -162,7 +163,19 @@ static void split_dims(int total, int parts, int* out) {   // quantization.py:38
 
 static void build_manifest(escb_handle* h) {
     const escb_config& c = h->cfg;
-    for (int q = 0; q < h->L; ++q) {
+    if (c.num_rvqs > 0) {
+        // RVQCodecs: quantizers = ProductResidualVectorQuantize at the bottleneck (base.py:73-85, quantization.py:139-168, 276-297)
+        const QuantDesc d = quant_desc(h, 0);
+        int vq[3];
+        split_dims(d.in_dim * d.in_freq * c.overlap, 3, vq);
+        for (int m = 0; m < 3; ++m) {
+            const std::string p = "quantizers.vqs." + std::to_string(m);
+            add_weight(h, p + ".proj_down.weight", {d.d, vq[m]});
+            add_weight(h, p + ".proj_up.weight", {vq[m], d.d});
+            for (int i = 0; i < c.num_rvqs; ++i) add_weight(h, p + ".vqs." + std::to_string(i) + ".embedding.weight", {c.codebook_size, d.d});
+        }
+    }
+    for (int q = 0; q < (c.num_rvqs > 0 ? 0 : h->L); ++q) {
         const QuantDesc d = quant_desc(h, q);
         int vq[3];
         split_dims(d.in_dim * d.in_freq * c.overlap, 3, vq);
@@ -482,17 +495,38 @@ static void pack_layer(Packer& P, int li) {
     }
 }
 
-static void pack_quant(Packer& P, int q) {
-    escb_handle* h = P.h;
-    const QuantDesc d = quant_desc(h, q);
-    QuantW& qw = h->quants[q];
-    const int C = d.in_dim, Hq = d.in_freq, dd = d.d, K = h->cfg.codebook_size;
+// normalised / transposed / raw forms of one codebook (codebook.py:32-40), appended to the three vectors
+static void pack_codebook(const std::vector<float>& e, int K, int dd, std::vector<float>& raw, std::vector<float>& cbt,
+                          std::vector<float>& cn) {
+    const size_t r0 = raw.size(), t0 = cbt.size(), n0 = cn.size();
+    raw.resize(r0 + (size_t)K * dd);
+    cbt.resize(t0 + (size_t)K * dd);
+    cn.resize(n0 + (size_t)K);
+    for (int c = 0; c < K; ++c) {
+        float ss = 0.f;
+        for (int j = 0; j < dd; ++j) { const float v = e[(size_t)c * dd + j]; ss = fmaf(v, v, ss); }
+        const float den = fmaxf(sqrtf(ss), 1e-12f);
+        float s2 = 0.f;
+        for (int j = 0; j < dd; ++j) {
+            const float v = e[(size_t)c * dd + j];
+            const float nv = v / den;
+            raw[r0 + (size_t)c * dd + j] = v;
+            cbt[t0 + (size_t)j * K + c] = nv;
+            s2 = fmaf(nv, nv, s2);
+        }
+        cn[n0 + c] = s2;
+    }
+}
+
+// The projections of one product quantizer (ESC's ProductVectorQuantize and RVQCodecs' ProductResidualVectorQuantize share
+// the frame geometry); `down_name(g)` / `up_name(g)` give the checkpoint keys of group g's weights.
+template <class FD, class FU>
+static void pack_projections(Packer& P, QuantW& qw, int C, int Hq, int dd, int K, FD down_name, FU up_name) {
     const int frame = 2 * C * Hq;
     int vq[3], start[3];
     split_dims(frame, 3, vq);
     start[0] = 0; start[1] = vq[0]; start[2] = vq[0] + vq[1];
     qw.in_dim = C; qw.in_freq = Hq; qw.d = dd; qw.frame_dim = frame; qw.ncodes = K;
-    const std::string p = "quantizers." + std::to_string(q);
     std::vector<float> down, up;
     Packer::init_gemm(qw.down, 3 * dd, frame, down);
     Packer::init_gemm(qw.up, frame, 3 * dd, up);
@@ -504,8 +538,8 @@ static void pack_quant(Packer& P, int q) {
                 const int kp = hh * 2 * C + o * C + c;
                 const int g = kref >= start[2] ? 2 : (kref >= start[1] ? 1 : 0);
                 const int kl = kref - start[g];
-                const std::vector<float>& dw = P.w(p + ".down_projs." + std::to_string(g) + ".weight");   // [d][vq_g]
-                const std::vector<float>& uw = P.w(p + ".up_projs." + std::to_string(g) + ".weight");     // [vq_g][d]
+                const std::vector<float>& dw = P.w(down_name(g));   // [d][vq_g]
+                const std::vector<float>& uw = P.w(up_name(g));     // [vq_g][d]
                 for (int j = 0; j < dd; ++j) {
                     down[(size_t)kp * qw.down.ldw + g * dd + j] = dw[(size_t)j * vq[g] + kl];
                     up[(size_t)(g * dd + j) * qw.up.ldw + kp] = uw[(size_t)kl * dd + j];
@@ -523,7 +557,7 @@ static void pack_quant(Packer& P, int q) {
         for (int g = 0; g < 3; ++g) {
             std::vector<float> dg;
             Packer::init_gemm(qw.down_g[g], dd, run * Hq, dg);
-            const std::vector<float>& dw = P.w(p + ".down_projs." + std::to_string(g) + ".weight");   // [d][vq_g]
+            const std::vector<float>& dw = P.w(down_name(g));   // [d][vq_g]
             for (int hh = 0; hh < Hq; ++hh)
                 for (int oc = g * run; oc < (g + 1) * run; ++oc) {
                     const int o = oc / C, c = oc - o * C;
@@ -534,28 +568,43 @@ static void pack_quant(Packer& P, int q) {
             P.put(&qw.down_g[g].wt, dg);
         }
     }
+}
+
+static void pack_quant(Packer& P, int q) {
+    escb_handle* h = P.h;
+    const QuantDesc d = quant_desc(h, q);
+    QuantW& qw = h->quants[q];
+    const int K = h->cfg.codebook_size;
+    const std::string p = "quantizers." + std::to_string(q);
+    pack_projections(P, qw, d.in_dim, d.in_freq, d.d, K,
+                     [&](int g) { return p + ".down_projs." + std::to_string(g) + ".weight"; },
+                     [&](int g) { return p + ".up_projs." + std::to_string(g) + ".weight"; });
     // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
-    std::vector<float> raw((size_t)3 * K * dd), cbt((size_t)3 * K * dd), cn((size_t)3 * K);
-    for (int g = 0; g < 3; ++g) {
-        const std::vector<float>& e = P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight");
-        for (int c = 0; c < K; ++c) {
-            float ss = 0.f;
-            for (int j = 0; j < dd; ++j) { const float v = e[(size_t)c * dd + j]; ss = fmaf(v, v, ss); }
-            const float den = fmaxf(sqrtf(ss), 1e-12f);
-            float s2 = 0.f;
-            for (int j = 0; j < dd; ++j) {
-                const float v = e[(size_t)c * dd + j];
-                const float nv = v / den;
-                raw[((size_t)g * K + c) * dd + j] = v;
-                cbt[((size_t)g * dd + j) * K + c] = nv;
-                s2 = fmaf(nv, nv, s2);
-            }
-            cn[(size_t)g * K + c] = s2;
-        }
-    }
+    std::vector<float> raw, cbt, cn;
+    for (int g = 0; g < 3; ++g) pack_codebook(P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight"), K, d.d, raw, cbt, cn);
     P.put(&qw.raw, raw);
     P.put(&qw.cbt, cbt);
     P.put(&qw.cnorm, cn);
+}
+
+// RVQCodecs: one ProductResidualVectorQuantize at the bottleneck, codebooks ordered [group][stream]
+static void pack_rvq(Packer& P) {
+    escb_handle* h = P.h;
+    const QuantDesc d = quant_desc(h, 0);
+    RvqW& w = h->rvq;
+    const int K = h->cfg.codebook_size, S = h->cfg.num_rvqs;
+    w.S = S;
+    pack_projections(P, w.q, d.in_dim, d.in_freq, d.d, K,
+                     [&](int g) { return "quantizers.vqs." + std::to_string(g) + ".proj_down.weight"; },
+                     [&](int g) { return "quantizers.vqs." + std::to_string(g) + ".proj_up.weight"; });
+    w.q.raw = w.q.cbt = w.q.cnorm = nullptr;
+    std::vector<float> raw, cbt, cn;
+    for (int g = 0; g < 3; ++g)
+        for (int i = 0; i < S; ++i)
+            pack_codebook(P.w("quantizers.vqs." + std::to_string(g) + ".vqs." + std::to_string(i) + ".embedding.weight"), K, d.d, raw, cbt, cn);
+    P.put(&w.raw, raw);
+    P.put(&w.cbt, cbt);
+    P.put(&w.cnorm, cn);
 }
 
 static void pack_front(Packer& P) {
@@ -665,6 +714,8 @@ struct Work {
     float* hid = nullptr;
     float2* stats = nullptr;                   // LayerNorm (mean, rstd) per logical GEMM row
     float* ze = nullptr;                       // projected VQ vectors [B*T][ldc(3d)]
+    float* zq = nullptr;                       // RVQCodecs: summed codewords [B*T][ldc(3d)]
+    float* se = nullptr;                       // RVQCodecs: eval-loss numerators [B*T][3]
     float* Y1 = nullptr;                       // de-embed pixel map [B][F][2W][ldc(C0)]
     long long* codes = nullptr;                // forward(): internal codes when the caller passes none
     float* dense = nullptr;                    // staging for the unit entry points
@@ -704,6 +755,10 @@ static size_t plan(const escb_handle* h, int B, int W, int T, int what, Bump& bp
     int dmax = 0;
     for (int q = 0; q < L; ++q) dmax = std::max(dmax, h->cfg.codebook_dims[q]);
     wk.ze = bp.take<float>((size_t)B * (W / 2) * ldc(3 * dmax));
+    if (h->cfg.num_rvqs > 0) {
+        wk.zq = bp.take<float>((size_t)B * (W / 2) * ldc(3 * dmax));
+        wk.se = bp.take<float>((size_t)B * (W / 2) * 3);
+    }
     if (what & WK_DEC) wk.Y1 = bp.take<float>((size_t)B * h->F * h->pt * W * ldc(h->C0));
     wk.codes = bp.take<long long>((size_t)B * L * 3 * (W / 2));
     if (what & WK_UNIT) {
@@ -864,6 +919,27 @@ static void run_csrvq_forward(Ctx& c, int S, long long* codes, float* loss) {
     }
 }
 
+// ---- RVQCodecs (codecs.py:96-181): encoder -> ProductResidualVectorQuantize at the bottleneck -> plain Decoder
+static void run_rvq_quantize(Ctx& c, int S, long long* codes, float* zq, float* se) {
+    const RvqW& w = c.h->rvq;
+    const int T = c.W / 2, ldz = ldc(3 * w.q.d);
+    op_pvq_down(c.L, w.q, c.wk.enc[c.h->L - 1], nullptr, c.B, c.W, c.wk.ze, ldz);            // pre_process + proj_down
+    op_rvq_chain(c.L, w, c.wk.ze, ldz, (long long)c.B * T, S, codes, T, zq, se);
+}
+
+// Decoder.forward (base.py:194-203) from the summed codewords: proj_up + post_process, then the up-sampling layers
+static void run_rvq_decoder(Ctx& c, const float* zq) {
+    escb_handle* h = c.h;
+    const int L = h->L;
+    op_rvq_up(c.L, h->rvq, zq, ldc(3 * h->rvq.q.d), c.B, c.W, c.wk.dec[L - 1]);
+    for (int i = 0; i < L - 1; ++i) {
+        const int lv = L - 1 - i;
+        run_layer(c, L + i, c.wk.dec[lv], c.wk.xw, c.wk.dec[lv - 1], h->lev[lv].H);
+    }
+}
+
+static int max_streams_of(const escb_handle* h) { return h->cfg.num_rvqs > 0 ? h->cfg.num_rvqs : h->L; }
+
 static int check_ready(const escb_handle* h) {
     if (!h) return fail(ESCB_EINVAL, "null handle");
     if (!h->finalized) return fail(ESCB_ESTATE, "escb_finalize() has not been called since the last weight change");
@@ -944,6 +1020,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (c.in_freq < 2 || c.in_freq % c.patch_freq) return fail(ESCB_EINVAL, "in_freq must be a multiple of patch_freq");
     if (c.mlp_hidden_mult < 1) return fail(ESCB_EINVAL, "mlp_hidden_mult must be >= 1");
     if (c.codebook_size < 1) return fail(ESCB_EINVAL, "codebook_size must be positive");
+    if (c.num_rvqs < 0 || c.num_rvqs > 64) return fail(ESCB_EINVAL, "num_rvqs must be in [0, 64]");
     const int n_fft = 2 * (c.in_freq - 1);
     if (c.win_length > n_fft || c.win_length < 1 || c.hop_length < 1 || c.win_length % c.hop_length ||
         (n_fft - c.win_length) % 2 || (c.hop_length & 3))
@@ -1046,7 +1123,8 @@ int escb_finalize(escb_handle* h) {
         if (!w.set) return fail(ESCB_ESTATE, "weight '%s' has not been set", w.name.c_str());
     Packer P{h};
     for (int li = 0; li < 2 * h->L; ++li) pack_layer(P, li);
-    for (int q = 0; q < h->L; ++q) pack_quant(P, q);
+    if (h->cfg.num_rvqs > 0) pack_rvq(P);
+    else for (int q = 0; q < h->L; ++q) pack_quant(P, q);
     pack_front(P);
     cudaSetDevice(h->device);
     if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
@@ -1086,7 +1164,7 @@ int escb_encode(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int32
                 size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!audio || !codes) return fail(ESCB_EINVAL, "null argument");
-    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
     int W = 0;
     if (int e = time_patches(h, Ls, &W)) return e;
     const int T = frames_of(h, Ls);
@@ -1094,7 +1172,8 @@ int escb_encode(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int32
     if (int e = begin(h, c, B, W, T, WK_ENC, ws, ws_bytes, stream)) return e;
     op_stft(c.L, h->front, audio, B, Ls, T, c.wk.Sf);
     run_encoder(c, T);
-    run_csrvq_encode(c, S, (long long*)codes);
+    if (h->cfg.num_rvqs > 0) run_rvq_quantize(c, S, (long long*)codes, nullptr, nullptr);
+    else run_csrvq_encode(c, S, (long long*)codes);
     return finish(c, "escb_encode");
 }
 
@@ -1102,10 +1181,13 @@ int escb_decode(escb_handle* h, const int64_t* codes, int32_t B, int32_t S, int3
                 void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!codes || (!audio && !recon_feat)) return fail(ESCB_EINVAL, "null argument");
-    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
     Ctx c;
     if (int e = begin(h, c, B, W, h->pt * W, WK_DEC, ws, ws_bytes, stream)) return e;
-    run_csrvq_decode(c, S, (const long long*)codes);
+    if (h->cfg.num_rvqs > 0) {
+        op_rvq_gather(c.L, h->rvq, (const long long*)codes, S, (long long)B * (W / 2), W / 2, c.wk.zq, ldc(3 * h->rvq.q.d));
+        run_rvq_decoder(c, c.wk.zq);
+    } else run_csrvq_decode(c, S, (const long long*)codes);
     run_backend(c, audio, recon_feat);
     return finish(c, "escb_decode");
 }
@@ -1114,7 +1196,7 @@ int escb_forward(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int3
                  float* raw_feat, float* recon_feat, float* vq_loss, void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!audio) return fail(ESCB_EINVAL, "null argument");
-    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
     int W = 0;
     if (int e = time_patches(h, Ls, &W)) return e;
     const int T = frames_of(h, Ls);
@@ -1127,7 +1209,11 @@ int escb_forward(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int3
         const cudaError_t e = cudaMemsetAsync(vq_loss, 0, (size_t)B * sizeof(float), c.L.st);
         if (e != cudaSuccess && c.L.err == cudaSuccess) c.L.err = e;
     }
-    run_csrvq_forward(c, S, codes ? (long long*)codes : c.wk.codes, vq_loss);
+    if (h->cfg.num_rvqs > 0) {
+        run_rvq_quantize(c, S, codes ? (long long*)codes : c.wk.codes, c.wk.zq, vq_loss ? c.wk.se : nullptr);
+        if (vq_loss) op_rvq_loss(c.L, c.wk.se, B, W / 2, h->rvq.q.d, vq_loss);
+        run_rvq_decoder(c, c.wk.zq);
+    } else run_csrvq_forward(c, S, codes ? (long long*)codes : c.wk.codes, vq_loss);
     run_backend(c, audio_out, recon_feat);
     return finish(c, "escb_forward");
 }
@@ -1151,7 +1237,7 @@ int escb_encode_host(escb_handle* h, const float* audio_host, int32_t B, int64_t
     if (int e = check_ready(h)) return e;
     if (!audio_host || !codes_host) return fail(ESCB_EINVAL, "null argument");
     if (B <= 0) return fail(ESCB_EINVAL, "batch must be positive");
-    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
     int W = 0;
     if (int e = time_patches(h, Ls, &W)) return e;
     size_t ws = 0;
@@ -1179,7 +1265,7 @@ int escb_decode_host(escb_handle* h, const int64_t* codes_host, int32_t B, int32
     if (int e = check_ready(h)) return e;
     if (!codes_host || !audio_host) return fail(ESCB_EINVAL, "null argument");
     if (B <= 0 || W <= 0) return fail(ESCB_EINVAL, "batch and W must be positive");
-    if (S < 1 || S > h->L) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", h->L);
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
     size_t ws = 0;
     if (int e = escb_workspace_bytes(h, B, W, &ws)) return e;
     const int64_t n_out = escb_decoded_samples(h, W);
@@ -1282,7 +1368,7 @@ int escb_pvq_encode(escb_handle* h, int32_t q, const float* enc, const float* de
                     void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!enc || !codes) return fail(ESCB_EINVAL, "null argument");
-    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    if (q < 0 || q >= h->L || h->cfg.num_rvqs > 0) return fail(ESCB_EINVAL, "stream index out of range");
     Ctx c;
     if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
     pvq_encode(c, q, enc, dec, (long long*)codes, 1, 0);
@@ -1293,7 +1379,7 @@ int escb_pvq_decode(escb_handle* h, int32_t q, const int64_t* codes, const float
                     void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!codes || !out) return fail(ESCB_EINVAL, "null argument");
-    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    if (q < 0 || q >= h->L || h->cfg.num_rvqs > 0) return fail(ESCB_EINVAL, "stream index out of range (the per-stream entry points are ESC's)");
     Ctx c;
     if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
     if (!(c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], nullptr, dec, B, W, (long long*)codes, 1, 0, out, nullptr, 0)))
@@ -1305,7 +1391,7 @@ int escb_pvq_stream(escb_handle* h, int32_t q, const float* enc, const float* de
                     float* out, void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!enc || !codes) return fail(ESCB_EINVAL, "null argument");
-    if (q < 0 || q >= h->L) return fail(ESCB_EINVAL, "stream index out of range");
+    if (q < 0 || q >= h->L || h->cfg.num_rvqs > 0) return fail(ESCB_EINVAL, "stream index out of range (the per-stream entry points are ESC's)");
     Ctx c;
     if (int e = begin(h, c, B, W, h->pt * W, WK_UNIT, ws, ws_bytes, stream)) return e;
     if (!(c.L.fuse_pvq && op_pvq_stream(c.L, h->quants[q], enc, dec, B, W, (long long*)codes, 1, 0, out, nullptr, 0))) {
@@ -1318,7 +1404,7 @@ int escb_pvq_stream(escb_handle* h, int32_t q, const float* enc, const float* de
 int escb_codebook_argmin(escb_handle* h, int32_t q, int32_t g, const float* z, int64_t rows, int64_t* idx, void* stream) {
     if (int e = check_ready(h)) return e;
     if (!z || !idx) return fail(ESCB_EINVAL, "null argument");
-    if (q < 0 || q >= h->L || g < 0 || g >= 3) return fail(ESCB_EINVAL, "stream/group index out of range");
+    if (q < 0 || q >= h->L || g < 0 || g >= 3 || h->cfg.num_rvqs > 0) return fail(ESCB_EINVAL, "stream/group index out of range");
     if (rows <= 0) return ESCB_OK;
     Ctx c;
     c.h = h;

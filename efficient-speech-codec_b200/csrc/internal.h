@@ -48,6 +48,17 @@ struct QuantW {
     const float* cnorm;                              // [3][ncodes] squared norms of cbn rows
 };
 
+// RVQCodecs: ProductResidualVectorQuantize at the bottleneck (quantization.py:276-378).  The projections reuse the
+// product-VQ layouts of QuantW (per-group down-projections, block-structured up-projection); every group owns `S`
+// residual codebooks.
+struct RvqW {
+    QuantW q;                                        // geometry + down_g / up; its own raw / cbt / cnorm are unused
+    int S;                                           // num_rvqs
+    const float* raw;                                // [3][S][ncodes][d]
+    const float* cbt;                                // [3][S][d][ncodes] L2-normalised, transposed
+    const float* cnorm;                              // [3][S][ncodes]
+};
+
 struct Conv3Weights { float w[9 * 64 * 2]; };        // [tap][c][2], c < kEmbedMaxC
 
 struct FrontW {
@@ -163,6 +174,12 @@ void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G,
 bool op_pvq_stream(Launcher& L, const QuantW& q, const float* enc, const float* dec, int B, int W, long long* codes, int S,
                    int s, float* out, float* ze, int ldz);
 cudaError_t pvq_init();
+// RVQCodecs (pvq.cu): residual chain on the projected vectors, code gather-sum for decode, eval-mode loss reduce
+void op_rvq_chain(Launcher& L, const RvqW& w, const float* ze, int ldz, long long rows, int S, long long* codes, int T,
+                  float* zq, float* se);
+void op_rvq_gather(Launcher& L, const RvqW& w, const long long* codes, int S, long long rows, int T, float* zq, int ldz);
+void op_rvq_up(Launcher& L, const RvqW& w, const float* zq, int ldz, int B, int W, float* out);
+void op_rvq_loss(Launcher& L, const float* se, int B, int T, int d, float* loss);
 void op_vq_loss(Launcher& L, const QuantW& q, const float* ze, int ldz, const long long* codes, int S, int s, int B,
                 int T, float* loss);
 

@@ -751,4 +751,184 @@ pvq_stream_kernel(const PvqStreamArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ RVQCodecs residual chain
+// ResidualVectorQuantize.quantize_to_code / residual_vector_quantization in eval mode (quantization.py:170-195, 223-237)
+// on the down-projected vectors of one group: for stream i = 0..S-1  code_i = argmin_i(residual)  (Codebook.quantize_to_code:
+// both sides L2-normalised, first minimum), residual -= raw_i[code_i].  One block = 32 rows x one group, the whole chain
+// stays in shared memory; the distance tile is codebook_argmin_kernel's.  Optionally emits z_q = sum_i raw_i[code_i]
+// (accumulated in stream order from 0, like `z_q = z_q + z_q_i`) and the eval-mode loss numerator
+// sum_i sum_j (raw_i[code_i][j] - residual_i[j])^2 per row.
+template <int D>
+__global__ void __launch_bounds__(256)
+rvq_chain_kernel(const float* __restrict__ ze, const int ldz, const float* __restrict__ cbt, const float* __restrict__ cnorm,
+                 const float* __restrict__ raw, const int ncodes, const int Stot, const int S, const long long rows,
+                 long long* __restrict__ codes, const int T, float* __restrict__ zq, float* __restrict__ se) {
+    __shared__ float res[kArgminRows][D + 1];                  // running residual
+    __shared__ float zqa[kArgminRows][D + 1];
+    __shared__ float sea[kArgminRows];
+    __shared__ __align__(16) float zs[D][kArgminRows];         // 2 * normalised residual, transposed
+    __shared__ float zzs[kArgminRows];
+    __shared__ __align__(16) float cbs[D][kArgminChunk];
+    __shared__ float cns[kArgminChunk];
+    __shared__ float redv[kArgminRows][2];
+    __shared__ int redi[kArgminRows][2];
+    const int tid = threadIdx.x, g = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * kArgminRows;
+    for (int i = tid; i < kArgminRows * D; i += 256) {
+        const int r = i / D, k = i - r * D;
+        const long long m = row0 + r;
+        res[r][k] = m < rows ? __ldg(ze + m * (long long)ldz + g * D + k) : 0.f;
+        zqa[r][k] = 0.f;
+    }
+    if (tid < kArgminRows) sea[tid] = 0.f;
+    __syncthreads();
+    const int cg = tid & 63, rg = tid >> 6;
+    const int lane = tid & 31, wsel = (tid >> 5) & 1;
+    for (int si = 0; si < S; ++si) {
+        if (tid < kArgminRows) {
+            float zn[D];
+            float ss = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { zn[k] = res[tid][k]; ss = fmaf(zn[k], zn[k], ss); }
+            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+            float zz = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float v = zn[k] / denom;
+                zz = fmaf(v, v, zz);
+                zs[k][tid] = 2.0f * v;
+            }
+            zzs[tid] = zz;
+        }
+        float best[8];
+        int besti[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { best[r] = 3.0e38f; besti[r] = 0x7fffffff; }
+        const float* cb = cbt + ((long long)g * Stot + si) * D * ncodes;
+        const float* cn = cnorm + ((long long)g * Stot + si) * ncodes;
+        for (int chunk = 0; chunk < ncodes; chunk += kArgminChunk) {
+            __syncthreads();
+            for (int i = tid; i < D * (kArgminChunk / 4); i += 256) {
+                const int k = i / (kArgminChunk / 4), c4 = (i % (kArgminChunk / 4)) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (chunk + c4 + 3 < ncodes) v = __ldg(reinterpret_cast<const float4*>(cb + (long long)k * ncodes + chunk + c4));
+                *reinterpret_cast<float4*>(&cbs[k][c4]) = v;
+            }
+            cns[tid] = (chunk + tid < ncodes) ? __ldg(cn + chunk + tid) : 3.0e38f;
+            __syncthreads();
+            float acc[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float4 c = *reinterpret_cast<const float4*>(&cbs[k][cg * 4]);
+                const float4 z0 = *reinterpret_cast<const float4*>(&zs[k][rg * 8]);
+                const float4 z1 = *reinterpret_cast<const float4*>(&zs[k][rg * 8 + 4]);
+                const float zr[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                const float cj[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(zr[r], cj[j], acc[r][j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int code = chunk + cg * 4 + j;
+                const float cnj = cns[cg * 4 + j];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float dist = (zzs[rg * 8 + r] - acc[r][j]) + cnj;
+                    if (dist < best[r]) { best[r] = dist; besti[r] = code; }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float bv = best[r];
+            int bi = besti[r];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { redv[rg * 8 + r][wsel] = bv; redi[rg * 8 + r][wsel] = bi; }
+        }
+        __syncthreads();
+        if (tid < kArgminRows) {
+            float bv = redv[tid][0];
+            int bi = redi[tid][0];
+            const float ov = redv[tid][1];
+            const int oi = redi[tid][1];
+            if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            if (bi == 0x7fffffff) bi = 0;
+            const long long m = row0 + tid;
+            if (m < rows) {
+                const long long b = m / T;
+                const int t = (int)(m - b * T);
+                codes[((b * S + si) * 3 + g) * (long long)T + t] = bi;
+            }
+            const float* e = raw + (((long long)g * Stot + si) * ncodes + bi) * D;
+            float sq = sea[tid];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float ev = __ldg(e + k), rv = res[tid][k];
+                const float d = ev - rv;
+                sq = fmaf(d, d, sq);
+                zqa[tid][k] = zqa[tid][k] + ev;
+                res[tid][k] = rv - ev;
+            }
+            sea[tid] = sq;
+        }
+        __syncthreads();
+    }
+    if (zq)
+        for (int i = tid; i < kArgminRows * D; i += 256) {
+            const int r = i / D, k = i - r * D;
+            if (row0 + r < rows) zq[(row0 + r) * (long long)ldz + g * D + k] = zqa[r][k];
+        }
+    if (se && tid < kArgminRows && row0 + tid < rows) se[(row0 + tid) * 3 + g] = sea[tid];
+}
+
+// RVQCodecs decode: z_q[row][g*d + j] = sum_i raw_i[codes[b, i, g, t]][j], in stream order from 0 (dequantize_code,
+// quantization.py:239-245).  Out-of-range indices are clamped and latched like ACodes.
+static __global__ void rvq_gather_kernel(const long long* __restrict__ codes, const float* __restrict__ raw, const int ncodes,
+                                         const int Stot, const int S, const int d, const long long rows, const int T,
+                                         float* __restrict__ zq, const int ldz, int* __restrict__ bad) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * 3 * d) return;
+    const int j = (int)(idx % d);
+    const int g = (int)((idx / d) % 3);
+    const long long m = idx / (3 * d), b = m / T;
+    const int t = (int)(m - b * T);
+    float acc = 0.f;
+    for (int si = 0; si < S; ++si) {
+        long long c = codes[((b * S + si) * 3 + g) * (long long)T + t];
+        if (c < 0 || c >= ncodes) { if (bad) *(volatile int*)bad = 1; c = 0; }
+        acc = acc + __ldg(raw + (((long long)g * Stot + si) * ncodes + c) * d + j);
+    }
+    zq[m * ldz + g * d + j] = acc;
+}
+
+// eval-mode VQ loss of RVQCodecs: loss[b] = sum_{t, g} se[b, t, g] / (T * d) / 3 (Codebook.forward mse over (T, d) per
+// stream, summed over streams, averaged over the 3 groups: quantization.py:184-186, 343-346), one block per clip
+static __global__ void rvq_loss_kernel(const float* __restrict__ se, const int T, const int d, float* __restrict__ loss) {
+    const int b = blockIdx.x;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < T * 3; i += blockDim.x) acc += se[(long long)b * T * 3 + i];
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) loss[b] = v / ((float)T * d) / 3.0f;
+    }
+}
+
 }  // namespace escb

@@ -145,6 +145,47 @@ bool op_pvq_stream(Launcher& L, const QuantW& q, const float* enc, const float* 
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ RVQCodecs
+void op_rvq_chain(Launcher& L, const RvqW& w, const float* ze, int ldz, long long rows, int S, long long* codes, int T,
+                  float* zq, float* se) {
+    const QuantW& q = w.q;
+    L.begin(OP_ARGMIN, 2.0 * rows * 3 * S * q.ncodes * q.d, rows * 3.0 * (4.0 * q.d + 8.0 * S));
+    dim3 grid((unsigned)((rows + kArgminRows - 1) / kArgminRows), 3);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (q.d) {
+#define X(n) case n: rvq_chain_kernel<n><<<grid, 256, 0, L.st>>>(ze, ldz, w.cbt, w.cnorm, w.raw, q.ncodes, w.S, S, rows, codes, T, zq, se); e = cudaGetLastError(); break;
+        ESCB_STREAM_DS(X)
+#undef X
+        default: break;
+    }
+    L.note(e);
+}
+
+void op_rvq_gather(Launcher& L, const RvqW& w, const long long* codes, int S, long long rows, int T, float* zq, int ldz) {
+    const long long total = rows * 3 * w.q.d;
+    L.begin(OP_LAYOUT, 0.0, 8.0 * rows * 3 * S + 4.0 * total);
+    rvq_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, L.st>>>(codes, w.raw, w.q.ncodes, w.S, S, w.q.d, rows, T, zq, ldz, L.code_err);
+    L.note(cudaGetLastError());
+}
+
+// proj_up of every group + post_process (quantization.py:366-377): the block-structured up-projection GEMM of the
+// product VQ with dense rows as its A operand
+void op_rvq_up(Launcher& L, const RvqW& w, const float* zq, int ldz, int B, int W, float* out) {
+    const QuantW& q = w.q;
+    ARows al{zq, ldz};
+    EpiFrame ep{out, nullptr, q.in_freq, W, q.in_dim};
+    const long long M = (long long)B * (W / 2);
+    L.begin(OP_PVQ_UP, 2.0 * M * q.frame_dim * q.d, 4.0 * M * (q.frame_dim + 3.0 * q.d));
+    if (L.pvq_tc) L.note(tc::launch<false, ARows, EpiFrame, kPvqUpWide>(L.st, al, noln(L), q.up, M, ep));
+    else L.note(GemmLauncher<false, ARows, EpiFrame, 8, 9>::launch(L.st, al, noln(L), q.up, M, ep));
+}
+
+void op_rvq_loss(Launcher& L, const float* se, int B, int T, int d, float* loss) {
+    L.begin(OP_VQLOSS, 3.0 * B * T, 4.0 * B * T * 3);
+    rvq_loss_kernel<<<B, 256, 0, L.st>>>(se, T, d, loss);
+    L.note(cudaGetLastError());
+}
+
 void op_code_histogram(Launcher& L, const long long* codes, int B, int S, int G, int T, int ncodes, float* counts) {
     L.begin(OP_LAYOUT, 0.0, 8.0 * B * S * G * T + 8.0 * S * G * ncodes);
     code_histogram_kernel<<<S * G, 256, (size_t)ncodes * sizeof(unsigned), L.st>>>(codes, B, S, G, T, ncodes, counts, L.code_err);

@@ -77,6 +77,9 @@ class ESC(nn.Module):
             window_size=window_size, mlp_ratio=mlp_ratio, overlap=overlap, group_size=group_size,
             codebook_size=codebook_size, codebook_dims=list(codebook_dims), l2norm=l2norm, backbone=backbone,
             kernel_size=list(kernel_size), conv_depth=conv_depth)
+        self._init_common(in_freq, in_dim, max_streams, h_dims)
+
+    def _init_common(self, in_freq, in_dim, max_streams, h_dims) -> None:
         # attributes the reference exposes (base.py:16-20, 70)
         self.in_freq, self.in_dim = in_freq, in_dim
         self.max_streams = max_streams
@@ -312,13 +315,36 @@ class ESC(nn.Module):
         return out if feat.is_cuda else out.cpu()
 
 
-model_dict = {"csvq+swinT": ESC, "csvq+conv": ESC}
+class RVQCodecs(ESC):
+    """The reference's RVQ ablation codec (esc/models/codecs.py:96-181): the same Swin encoder, ONE
+    ``ProductResidualVectorQuantize`` at the bottleneck (``num_rvqs`` residual codebooks per group in the projected
+    space, esc/modules/vq/quantization.py:139-378) and the plain up-sampling ``Decoder`` (esc/models/base.py:161-203).
+    Same ``encode`` / ``decode`` / ``forward`` (eval) surface and code tensor shape ``[Bs, num_streams, group_size, T]``;
+    the native library runs it through the kernels of the ESC path plus a residual-chain kernel."""
+
+    def __init__(self, in_dim: int = 2, in_freq: int = 192, h_dims: list = [45, 72, 96, 144, 192, 384], max_streams: int = 6,
+                 backbone: str = 'transformer', kernel_size: list = [5, 2], conv_depth: int = 1, patch_size: list = [3, 2],
+                 swin_heads: list = [3, 6, 12, 24, 24], swin_depth: int = 2, window_size: int = 4, mlp_ratio: float = 4.,
+                 overlap: int = 2, num_rvqs: int = 6, group_size: int = 3, codebook_dim: int = 8, codebook_size: int = 1024,
+                 l2norm: bool = True, win_len: int = 20, hop_len: int = 5, sr: int = 16000) -> None:
+        nn.Module.__init__(self)
+        self.spec = CodecSpec.from_rvq_kwargs(
+            in_dim=in_dim, in_freq=in_freq, h_dims=list(h_dims), max_streams=max_streams, backbone=backbone,
+            kernel_size=list(kernel_size), conv_depth=conv_depth, patch_size=list(patch_size), swin_heads=list(swin_heads),
+            swin_depth=swin_depth, window_size=window_size, mlp_ratio=mlp_ratio, overlap=overlap, num_rvqs=num_rvqs,
+            group_size=group_size, codebook_dim=codebook_dim, codebook_size=codebook_size, l2norm=l2norm, win_len=win_len,
+            hop_len=hop_len, sr=sr)
+        self._init_common(in_freq, in_dim, max_streams, h_dims)
+        self.dims = 3
+
+
+model_dict = {"csvq+swinT": ESC, "csvq+conv": ESC, "rvq+swinT": RVQCodecs, "rvq+conv": RVQCodecs}
 
 
 def make_model(model_config, model_name: str = "csvq+swinT"):
     """codecs.py:190-200.  ``model_name`` defaults to ``csvq+swinT`` so the reference's own one-argument call in
     scripts/compress.py:22 works; the ``rvq+*`` families are the reference's ablation baselines."""
     if model_name not in model_dict:
-        raise NotImplementedError(f"{model_name}: only csvq+swinT (ESC) is accelerated by esc-b200")
+        raise NotImplementedError(f"{model_name} is not valid within [csvq+conv, csvq+swinT, rvq+conv, rvq+swinT]")
     cfg = model_config if isinstance(model_config, dict) else vars(model_config)
     return model_dict[model_name](**cfg)

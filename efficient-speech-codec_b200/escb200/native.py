@@ -13,7 +13,7 @@ import os
 from typing import List, Optional
 
 ESCB_MAX_LEVELS = 8
-ESCB_ABI_VERSION = 1
+ESCB_ABI_VERSION = 2
 _LIB_NAME = "libescb200.so"
 
 ERROR_NAMES = {0: "ESCB_OK", -1: "ESCB_EINVAL", -2: "ESCB_ENODEV", -3: "ESCB_ECUDA", -4: "ESCB_ESTATE",
@@ -48,7 +48,7 @@ class EscbConfig(C.Structure):
         ("h_dims", C.c_int32 * ESCB_MAX_LEVELS), ("swin_heads", C.c_int32 * ESCB_MAX_LEVELS),
         ("swin_depth", C.c_int32), ("window_size", C.c_int32), ("mlp_hidden_mult", C.c_int32),
         ("overlap", C.c_int32), ("group_size", C.c_int32), ("codebook_size", C.c_int32),
-        ("codebook_dims", C.c_int32 * ESCB_MAX_LEVELS), ("l2norm", C.c_int32),
+        ("codebook_dims", C.c_int32 * ESCB_MAX_LEVELS), ("l2norm", C.c_int32), ("num_rvqs", C.c_int32),
     ]
 
 
@@ -150,6 +150,7 @@ def make_config(spec) -> EscbConfig:
     cfg.group_size = spec.group_size
     cfg.codebook_size = spec.codebook_size
     cfg.l2norm = 1 if spec.l2norm else 0
+    cfg.num_rvqs = int(getattr(spec, "num_rvqs", 0)) if getattr(spec, "rvq", False) else 0
     return cfg
 
 

@@ -28,6 +28,13 @@ _ESC_DEFAULTS = dict(
     codebook_size=1024, codebook_dims=[8, 8, 8, 8, 8, 8], l2norm=True,
     backbone="transformer", kernel_size=[5, 2], conv_depth=1,
 )
+# RVQCodecs.__init__ (esc/models/codecs.py:98-119): one codebook_dim, num_rvqs residual codebooks per group
+_RVQ_DEFAULTS = dict(
+    in_dim=2, in_freq=192, h_dims=[45, 72, 96, 144, 192, 384], max_streams=6, backbone="transformer",
+    kernel_size=[5, 2], conv_depth=1, patch_size=[3, 2], swin_heads=[3, 6, 12, 24, 24], swin_depth=2, window_size=4,
+    mlp_ratio=4.0, overlap=2, num_rvqs=6, group_size=3, codebook_dim=8, codebook_size=1024, l2norm=True,
+    win_len=20, hop_len=5, sr=16000,
+)
 
 
 @dataclass(frozen=True)
@@ -106,6 +113,8 @@ class CodecSpec:
     kernel_size: Sequence[int] = (5, 2)
     conv_depth: int = 1
     extra: Dict = field(default_factory=dict)
+    rvq: bool = False          # RVQCodecs (codecs.py:96-181): one ProductResidualVectorQuantize at the bottleneck
+    num_rvqs: int = 0
 
     # ------------------------------------------------------------------ ctor
     @classmethod
@@ -118,6 +127,24 @@ class CodecSpec:
         merged.update(cfg)
         spec = cls(**merged)
         spec.validate()
+        return spec
+
+    @classmethod
+    def from_rvq_kwargs(cls, **cfg) -> "CodecSpec":
+        """Geometry of ``RVQCodecs(**cfg)``; ``codebook_dims`` is the single ``codebook_dim`` repeated."""
+        merged = dict(_RVQ_DEFAULTS)
+        unknown = set(cfg) - set(merged)
+        if unknown:
+            raise TypeError(f"RVQCodecs.__init__() got an unexpected keyword argument '{sorted(unknown)[0]}'")
+        merged.update(cfg)
+        d, n = merged.pop("codebook_dim"), merged.pop("num_rvqs")
+        if isinstance(d, (list, tuple)):
+            # configs/ablations/9kbps_rvq_conv.yaml passes a list; the reference fails inside nn.Embedding with a TypeError
+            raise TypeError("empty() received an invalid combination of arguments - codebook_dim must be an int")
+        spec = cls(**merged, codebook_dims=[int(d)] * merged["max_streams"], rvq=True, num_rvqs=int(n))
+        spec.validate()
+        if spec.num_rvqs < 1:
+            raise ValueError("num_rvqs must be positive")
         return spec
 
     def validate(self) -> None:
@@ -263,14 +290,23 @@ class CodecSpec:
         return e
 
     def manifest(self) -> List[ManifestEntry]:
-        """Every tensor of a reference ESC checkpoint's ``model_state_dict``."""
+        """Every tensor of a reference ESC (or RVQCodecs) checkpoint's ``model_state_dict``."""
         C0 = self.h_dims[0]
         pf, pt = self.patch_size
         e: List[ManifestEntry] = [
             ManifestEntry("ft.window", (self.win_length,), "window", True),
             ManifestEntry("ift.window", (self.win_length,), "window", True),
         ]
-        for q in self.quantizers():
+        if self.rvq:
+            # ProductResidualVectorQuantize (quantization.py:276-297) of ResidualVectorQuantize (:139-168) at the bottleneck
+            q0 = self.quantizers()[0]
+            for m in range(q0.groups):
+                p = f"quantizers.vqs.{m}"
+                e.append(ManifestEntry(f"{p}.proj_down.weight", (q0.codebook_dim, q0.vq_dims[m]), "linear_w"))
+                e.append(ManifestEntry(f"{p}.proj_up.weight", (q0.vq_dims[m], q0.codebook_dim), "linear_w"))
+                for i in range(self.num_rvqs):
+                    e.append(ManifestEntry(f"{p}.vqs.{i}.embedding.weight", (q0.codebook_size, q0.codebook_dim), "codebook"))
+        for q in ([] if self.rvq else self.quantizers()):
             for g in range(q.groups):
                 e.append(ManifestEntry(f"{q.prefix}.vqs.{g}.embedding.weight", (q.codebook_size, q.codebook_dim), "codebook"))
             for g in range(q.groups):

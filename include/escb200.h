@@ -34,7 +34,7 @@ extern "C" {
 #define ESCB_API
 #endif
 
-#define ESCB_ABI_VERSION 1
+#define ESCB_ABI_VERSION 2
 #define ESCB_MAX_LEVELS 8
 #define ESCB_MAX_DEPTH 8
 #define ESCB_NUM_OPS 20
@@ -67,6 +67,10 @@ typedef struct escb_config {
     int32_t codebook_size;                  /* 1024                                                             */
     int32_t codebook_dims[ESCB_MAX_LEVELS]; /* per stream                                                       */
     int32_t l2norm;                         /* 1: cosine-style argmin (only value supported)                    */
+    int32_t num_rvqs;                       /* 0: ESC (cross-scale product VQ, codecs.py:9-94).  > 0: RVQCodecs
+                                             * (codecs.py:96-181): ONE ProductResidualVectorQuantize at the bottleneck
+                                             * with num_rvqs residual codebooks per group of dimension codebook_dims[0]
+                                             * (quantization.py:139-378) and the plain Decoder (base.py:161-203)      */
 } escb_config;
 
 typedef struct escb_handle escb_handle;

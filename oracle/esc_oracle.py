@@ -400,3 +400,92 @@ class EscOracle:
         return {"cm_loss": cm_loss, "cb_loss": cb_loss, "raw_audio": x,
                 "recon_audio": self.audio_reconstruct(recon_feat), "raw_feat": planes,
                 "recon_feat": recon_feat, "codes": torch.stack(codes, dim=1)}
+
+
+# --------------------------------------------------------------------------- RVQCodecs (the reference's RVQ ablation codec)
+def rvq_project(sd: Dict[str, Tensor], z: Tensor, in_freq: int, cfg: OracleConfig) -> List[Tensor]:
+    """pre_process + per-group ``proj_down`` of ProductResidualVectorQuantize — quantization.py:343-353, 388-409."""
+    f = pvq_frames(z, in_freq, cfg.overlap)
+    dims = _split_dimension(f.shape[-1], cfg.group_size)
+    out, s = [], 0
+    for m, n in enumerate(dims):
+        out.append(F.linear(f[..., s:s + n], sd[f"quantizers.vqs.{m}.proj_down.weight"]))
+        s += n
+    return out
+
+
+def rvq_chain(sd: Dict[str, Tensor], m: int, z: Tensor, num_streams: int, cfg: OracleConfig):
+    """One group's residual chain in eval mode — ResidualVectorQuantize.residual_vector_quantization, quantization.py:170-195
+    (== quantize_to_code :223-237 for the codes).  Returns (z_q, codes [B, S, T], loss [B])."""
+    z_q, codes, loss = 0.0, [], 0.0
+    residual = z
+    for i in range(num_streams):
+        table = sd[f"quantizers.vqs.{m}.vqs.{i}.embedding.weight"]
+        code = codebook_argmin(residual, table, cfg.l2norm)
+        z_q_i = F.embedding(code, table)
+        loss = loss + F.mse_loss(z_q_i, residual, reduction="none").mean([1, 2])      # codebook.py:71-73 (eval)
+        residual = residual - z_q_i
+        z_q = z_q + z_q_i
+        codes.append(code)
+    return z_q, torch.stack(codes, dim=1), loss
+
+
+class RvqOracle(EscOracle):
+    """encode / decode / forward(eval) of the reference ``RVQCodecs`` (codecs.py:96-181) on a plain state dict."""
+
+    def __init__(self, cfg_kwargs: dict, state_dict: Dict[str, Tensor]):
+        kw = dict(cfg_kwargs)
+        self.num_rvqs = int(kw.pop("num_rvqs", 6))
+        d = kw.pop("codebook_dim", 8)
+        super().__init__(dict(kw, codebook_dims=[d] * kw.get("max_streams", 6)), state_dict)
+
+    def _quantize(self, z: Tensor, num_streams: int):
+        c = self.cfg
+        H0 = c.quantizer_geometry(0)[1]
+        ze = rvq_project(self.sd, z, H0, c)
+        parts, codes, loss = [], [], 0.0
+        for m in range(c.group_size):
+            zq_m, codes_m, loss_m = rvq_chain(self.sd, m, ze[m], num_streams, c)
+            parts.append(zq_m)
+            codes.append(codes_m)
+            loss = loss + loss_m
+        return parts, torch.stack(codes, dim=2), loss / c.group_size            # codes [B, S, groups, T]
+
+    def _dequantize(self, parts: List[Tensor]) -> Tensor:
+        c = self.cfg
+        ups = [F.linear(p, self.sd[f"quantizers.vqs.{m}.proj_up.weight"]) for m, p in enumerate(parts)]
+        return pvq_unframes(torch.cat(ups, dim=-1), c.quantizer_geometry(0)[1], c.overlap)
+
+    def _decoder(self, z_q: Tensor, feat_shape: Tuple[int, int]) -> Tensor:
+        """Decoder.forward — base.py:194-203."""
+        c = self.cfg
+        H, W = feat_shape
+        for i in range(len(c.h_dims) - 1):
+            z_q, H, W = self._layer(f"decoder.blocks.{i}", z_q, H, W, c.dec_heads[i], "up")
+        z_q, H, W = self._layer("decoder.post_nn", z_q, H, W, c.dec_heads[-1], None)
+        return patch_deembed(self.sd, z_q, c)
+
+    @torch.no_grad()
+    def encode(self, x: Tensor, num_streams: int = 6):
+        enc_hs, feat_shape = self.encoder(self.spec_transform(x))
+        return self._quantize(enc_hs[-1], num_streams)[1], feat_shape
+
+    @torch.no_grad()
+    def decode(self, codes: Tensor, feat_shape: Tuple[int, int]) -> Tensor:
+        c = self.cfg
+        parts = []
+        for m in range(c.group_size):                                          # dequantize_code, quantization.py:239-245
+            z_q = 0.0
+            for i in range(codes.shape[1]):
+                z_q = z_q + F.embedding(codes[:, i, m, :], self.sd[f"quantizers.vqs.{m}.vqs.{i}.embedding.weight"])
+            parts.append(z_q)
+        return self.audio_reconstruct(self._decoder(self._dequantize(parts), feat_shape))
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, x_feat: Optional[Tensor] = None, num_streams: int = 6) -> dict:
+        planes = self.spec_transform(x) if x_feat is None else x_feat.permute(0, 3, 1, 2)
+        enc_hs, feat_shape = self.encoder(planes)
+        parts, codes, loss = self._quantize(enc_hs[-1], num_streams)
+        recon_feat = self._decoder(self._dequantize(parts), feat_shape)
+        return {"cm_loss": loss, "cb_loss": loss, "raw_audio": x, "recon_audio": self.audio_reconstruct(recon_feat),
+                "raw_feat": planes, "recon_feat": recon_feat, "codes": codes}

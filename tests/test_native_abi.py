@@ -32,8 +32,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_layout_matches_header():
-    # 6 + 8 + 8 + 6 + 8 + 1 int32 fields
-    assert ctypes.sizeof(native.EscbConfig) == 4 * (6 + 8 + 8 + 6 + 8 + 1)
+    # 6 + 8 + 8 + 6 + 8 + 2 int32 fields
+    assert ctypes.sizeof(native.EscbConfig) == 4 * (6 + 8 + 8 + 6 + 8 + 2)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -67,7 +67,8 @@ def test_ctor_rejects_what_the_reference_rejects():
     with pytest.raises(TypeError):
         ESC(codebook_dim=8)                       # configs/ablations/9kbps_csvq_conv.yaml:21 vs codecs.py:16
     with pytest.raises(NotImplementedError):
-        make_model({}, "rvq+swinT")
+        make_model({}, "dac+base")                # not one of the reference's four model names
+    assert type(make_model({}, "rvq+swinT")).__name__ == "RVQCodecs"
     m = make_model(dict(swin_depth=4))
     assert m.max_streams == 6 and m.max_bps == 9.0
     with pytest.raises(AssertionError, match="multiple of overlap"):
