@@ -270,10 +270,17 @@ __device__ __forceinline__ uint32_t make_idesc(int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Round to tf32 (nearest, ties away): cvt.rna.tf32.f32 compiles to five SASS instructions (its NaN / infinity handling:
+// FSETP + IADD + LOP3 + SEL ...); for the finite values of this path the same bits come out of "add half an ulp of the
+// 10-bit mantissa, clear the 13 low bits" in two.  ESCB_TF32_CVT restores the instruction (A/B builds).
 __device__ __forceinline__ float tf32_rna(float x) {
+#ifdef ESCB_TF32_CVT
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
+#else
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#endif
 }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi.x = tf32_rna(v.x); lo.x = tf32_rna(v.x - hi.x);
