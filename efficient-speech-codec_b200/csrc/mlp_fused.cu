@@ -15,7 +15,7 @@ struct Params {
     int nch;                        // hidden chunks: ceil(4C / 64)
     int N2;                         // C rounded up to 16: UMMA N of fc2 / ACC2 columns
     int nx, na1, nl, nacc;          // ring depths: x slots, A1 buffers, L buffers, ACC2 buffers
-    int resident, ns;               // weights resident in smem | ring slots when streamed
+    int resident, ns1, ns2;         // weights resident in smem | ring slots of the fc1 / fc2 rings when streamed
     int nboxf, rem;                 // x tile = nboxf full 32-column boxes + a remainder of `rem` columns (dense rows)
     unsigned st2_bytes, slot_bytes, chunk_bytes, xslot_bytes;
     int col_a1, col_r, col_l, col_acc;
@@ -117,21 +117,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// The MMA warp's op order over the CTA's chunk stream c = 0 .. total-1 (chunk c belongs to tile c / nch): G2 of a chunk
-// is issued two chunks behind G1, except that with a single A1 buffer the G2s of a tile are drained before the first G1 of
-// the next one (its LayerNorm cannot start until the last G1 of this tile has released A1, and the in-order issuer
-// must not sit on that wait with G2 work behind it).  The weight loader walks the same order.
-template <class F1, class F2>
-__device__ __forceinline__ void for_each_op(int total, int nch, int na1, F1 g1, F2 g2) {
-    int pend = 0;
-    for (int c = 0; c < total; ++c) {
-        const int limit = (na1 == 1 && c % nch == 0) ? c - 1 : c - 2;
-        while (pend <= limit) g2(pend++);
-        g1(c);
-    }
-    while (pend < total) g2(pend++);
-}
-
 // Compile-time geometry of one channel width (the same arithmetic as make_plan): every per-row loop below unrolls
 // completely, so the shared-memory reads of a pass are issued back to back instead of one per loop trip.
 template <int C_>
@@ -164,8 +149,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sX = smem_u32(smem);
-    const uint32_t sW = sX + (uint32_t)p.nx * p.xslot_bytes;
-    const uint32_t w_bytes = p.resident ? (uint32_t)NCH * CHUNK : (uint32_t)p.ns * p.slot_bytes;
+    // weights: fc1 region, then fc2 region (resident: every stage of a tile at a fixed place; streamed: two rings)
+    const uint32_t sW1 = sX + (uint32_t)p.nx * p.xslot_bytes;
+    const uint32_t w1_bytes = p.resident ? (uint32_t)NCH * G::FC1 : (uint32_t)p.ns1 * ST1_BYTES;
+    const uint32_t sW2 = sW1 + w1_bytes;
+    const uint32_t w_bytes = w1_bytes + (p.resident ? (uint32_t)NCH * 2u * ST2 : (uint32_t)p.ns2 * ST2);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nx * p.xslot_bytes + w_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
     const uint32_t bar0 = smem_u32(bars);
@@ -183,7 +171,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
             mbar_init(bar(B_ACCFULL + i), 1); mbar_init(bar(B_ACCFREE + i), 4);
         }
         mbar_init(bar(B_LFREE), 1);
-        for (int i = 0; i < MAX_WST; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WFREE + i), 1); }
+        mbar_init(bar(B_RFREE), 1); mbar_init(bar(B_RFREE + 1), 1);
+        for (int i = 0; i < MAX_WST; ++i) {
+            mbar_init(bar(B_W1FULL + i), 1); mbar_init(bar(B_W1FREE + i), 1);
+            mbar_init(bar(B_W2FULL + i), 1); mbar_init(bar(B_W2FREE + i), 1);
+        }
         fence_barrier_init();
     }
     tc_fence_before();
@@ -217,44 +209,47 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
             }
         }
         __syncwarp();
-    } else if (warp == W_WLOAD) {
-        // ================================================================================ weight loader
+    } else if (warp == W_WLOAD1 || warp == W_WLOAD2) {
+        // ================================================================================ weight loaders (fc1 | fc2)
         if (elect_one() && my_tiles > 0) {
             const uint8_t* img = reinterpret_cast<const uint8_t*>(p.w_img);
+            const bool fc1 = warp == W_WLOAD1;
+            const int nst = fc1 ? NKB1 : 2;                                      // stages per chunk
+            const uint32_t sbase = fc1 ? sW1 : sW2;
+            const int bfull = fc1 ? B_W1FULL : B_W2FULL, bfree = fc1 ? B_W1FREE : B_W2FREE;
             if (p.resident) {
-                int st = 0;
                 for (int j = 0; j < NCH; ++j) {
-                    uint32_t off = (uint32_t)j * CHUNK;
-                    for (int kb = 0; kb < NKB1 + 2; ++kb, ++st) {
-                        const uint32_t bytes = kb < NKB1 ? G::st1_bytes(kb) : ST2;
-                        mbar_expect_tx(bar(B_WFULL + st), bytes);
-                        bulk_g2s(sW + off, img + off, bytes, bar(B_WFULL + st));
-                        off += bytes;
+                    uint32_t goff = (uint32_t)j * CHUNK + (fc1 ? 0u : G::FC1);
+                    uint32_t soff = (uint32_t)j * (fc1 ? G::FC1 : 2u * ST2);
+                    for (int kb = 0; kb < nst; ++kb) {
+                        const uint32_t bytes = fc1 ? G::st1_bytes(kb) : ST2;
+                        mbar_expect_tx(bar(bfull + j * nst + kb), bytes);
+                        bulk_g2s(sbase + soff, img + goff, bytes, bar(bfull + j * nst + kb));
+                        goff += bytes;
+                        soff += bytes;
                     }
                 }
             } else {
+                const uint32_t slot_bytes = fc1 ? (uint32_t)ST1_BYTES : ST2;
+                const uint32_t nslots = (uint32_t)(fc1 ? p.ns1 : p.ns2);
                 uint32_t slot = 0, phase = 0;
-                auto load = [&](uint32_t goff, uint32_t bytes) {
-                    mbar_wait_fast<256>(bar(B_WFREE + slot), phase ^ 1);
-                    mbar_expect_tx(bar(B_WFULL + slot), bytes);
-                    bulk_g2s(sW + slot * p.slot_bytes, img + goff, bytes, bar(B_WFULL + slot));
-                    if (++slot == (uint32_t)p.ns) { slot = 0; phase ^= 1; }
-                };
-                for_each_op(total, NCH, p.na1,
-                    [&](int c) {
-                        const uint32_t base = (uint32_t)(c % NCH) * CHUNK;
-                        for (int kb = 0; kb < NKB1; ++kb) load(base + kb * ST1_BYTES, G::st1_bytes(kb));
-                    },
-                    [&](int c) {
-                        const uint32_t base = (uint32_t)(c % NCH) * CHUNK + G::FC1;
-                        for (int kb = 0; kb < 2; ++kb) load(base + kb * ST2, ST2);
-                    });
+                for (int c = 0; c < total; ++c) {
+                    uint32_t goff = (uint32_t)(c % NCH) * CHUNK + (fc1 ? 0u : G::FC1);
+                    for (int kb = 0; kb < nst; ++kb) {
+                        const uint32_t bytes = fc1 ? G::st1_bytes(kb) : ST2;
+                        mbar_wait_fast<256>(bar(bfree + slot), phase ^ 1);
+                        mbar_expect_tx(bar(bfull + slot), bytes);
+                        bulk_g2s(sbase + slot * slot_bytes, img + goff, bytes, bar(bfull + slot));
+                        goff += bytes;
+                        if (++slot == nslots) { slot = 0; phase ^= 1; }
+                    }
+                }
             }
         }
         __syncwarp();
-    } else if (warp == W_MMA) {
-        // ================================================================================ MMA issuer
-        const uint32_t idesc1 = make_idesc(HC), idesc2 = make_idesc(N2);
+    } else if (warp == W_MMA1) {
+        // ================================================================================ MMA issuer 1: G1(c), R[c % 2] = A1 * W1[chunk]^T
+        const uint32_t idesc1 = make_idesc(HC);
         uint32_t wslot = 0, wphase = 0;
         // one K block of fc1: 3 MMAs per k-step into R (A = the LayerNorm images in TMEM)
         auto issue1 = [&](uint32_t saddr, int kb, uint32_t a_hi, uint32_t a_lo, uint32_t d) {
@@ -267,10 +262,54 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
                 const uint32_t ac = (uint32_t)((4 * kb + ks) * 8);
                 const uint64_t adv = (uint64_t)(ks * 2);
                 umma_ts_tf32(d, a_lo + ac, b_hi + adv, idesc1, (kb | ks) ? 1u : 0u);
+                if (p.dbg & 4) continue;
                 umma_ts_tf32(d, a_hi + ac, b_lo + adv, idesc1, 1u);
                 umma_ts_tf32(d, a_hi + ac, b_hi + adv, idesc1, 1u);
             }
         };
+        for (int c = 0; c < total; ++c) {
+            const int t = c / NCH, j = c - t * NCH, a = p.na1 == 2 ? t & 1 : 0;
+            MF_TL(1, c);
+            if (j == 0) MF_WAIT(0, bar(B_A1FULL + a), (uint32_t)((p.na1 == 2 ? t >> 1 : t) & 1));
+            MF_WAIT(1, bar(B_RFREE + (c & 1)), (uint32_t)(((c >> 1) & 1) ^ 1));      // G2(c - 2) has consumed R[c % 2] (and its lo twin)
+            const uint32_t a_hi = tmem + (uint32_t)(p.col_a1 + a * 2 * KP16), a_lo = a_hi + (uint32_t)KP16;
+            const uint32_t d = tmem + (uint32_t)(p.col_r + (c & 1) * HC);
+            if (p.resident) {
+                // the images were loaded once: only the first tile has to wait for them
+                if (c < NCH)
+                    for (int kb = 0; kb < NKB1; ++kb) MF_WAIT(3, bar(B_W1FULL + j * NKB1 + kb), 0u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t base = sW1 + (uint32_t)j * G::FC1;
+#pragma unroll
+                    for (int kb = 0; kb < NKB1; ++kb) issue1(base + (uint32_t)kb * ST1_BYTES, kb, a_hi, a_lo, d);
+                    umma_commit(bar(B_RFULL + (c & 1)));
+                    if (j + 1 == NCH) umma_commit(bar(B_A1FREE + a));
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int kb = 0; kb < NKB1; ++kb) {
+                    MF_WAIT(3, bar(B_W1FULL + wslot), wphase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue1(sW1 + wslot * ST1_BYTES, kb, a_hi, a_lo, d);
+                        umma_commit(bar(B_W1FREE + wslot));
+                        if (kb + 1 == NKB1) {
+                            umma_commit(bar(B_RFULL + (c & 1)));
+                            if (j + 1 == NCH) umma_commit(bar(B_A1FREE + a));
+                        }
+                    }
+                    __syncwarp();
+                    if (++wslot == (uint32_t)p.ns1) { wslot = 0; wphase ^= 1; }
+                }
+            }
+            MF_TL(2, c);
+        }
+    } else if (warp == W_MMA2) {
+        // ================================================================================ MMA issuer 2: G2(c), ACC2 += GELU chunk * W2[:, chunk]^T
+        const uint32_t idesc2 = make_idesc(N2);
+        uint32_t wslot = 0, wphase = 0;
         // one K block of fc2: A = the GELU chunk (hi in R, lo in L), accumulating into ACC2
         auto issue2 = [&](uint32_t saddr, int kb, uint32_t a_hi, uint32_t a_lo, uint32_t d, bool first) {
             const uint64_t b_hi = make_desc(saddr), b_lo = make_desc(saddr + (uint32_t)N2 * 128);
@@ -279,89 +318,52 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
                 const uint32_t ac = (uint32_t)((4 * kb + ks) * 8);
                 const uint64_t adv = (uint64_t)(ks * 2);
                 umma_ts_tf32(d, a_lo + ac, b_hi + adv, idesc2, (first && kb == 0 && ks == 0) ? 0u : 1u);
+                if (p.dbg & 4) continue;
                 umma_ts_tf32(d, a_hi + ac, b_lo + adv, idesc2, 1u);
                 umma_ts_tf32(d, a_hi + ac, b_hi + adv, idesc2, 1u);
             }
         };
-        for_each_op(total, NCH, p.na1,
-            [&](int c) {                                                           // G1(c): R[c % 2] = A1 * W1[chunk]^T
-                const int t = c / NCH, j = c % NCH, a = p.na1 == 2 ? t & 1 : 0;
-                MF_TL(1, c);
-                if (j == 0) MF_WAIT(0, bar(B_A1FULL + a), (uint32_t)((p.na1 == 2 ? t >> 1 : t) & 1));
-                const uint32_t a_hi = tmem + (uint32_t)(p.col_a1 + a * 2 * KP16), a_lo = a_hi + (uint32_t)KP16;
-                const uint32_t d = tmem + (uint32_t)(p.col_r + (c & 1) * HC);
-                if (p.resident) {
-                    // the images were loaded once: only the first tile has to wait for them (a try_wait costs ~300 clk even
-                    // on a completed phase, and this warp paid it four times per chunk)
-                    if (c < NCH)
-                        for (int kb = 0; kb < NKB1; ++kb) MF_WAIT(3, bar(B_WFULL + j * (NKB1 + 2) + kb), 0u);
+        for (int c = 0; c < total; ++c) {
+            const int t = c / NCH, j = c - t * NCH, ab = p.nacc == 2 ? t & 1 : 0;
+            MF_WAIT(1, bar(B_HFULL + (c & 1)), (uint32_t)((c >> 1) & 1));
+            if (j == 0) MF_WAIT(2, bar(B_ACCFREE + ab), (uint32_t)(((p.nacc == 2 ? t >> 1 : t) & 1) ^ 1));
+            const uint32_t a_hi = tmem + (uint32_t)(p.col_r + (c & 1) * HC);
+            const uint32_t a_lo = tmem + (uint32_t)(p.col_l + (p.nl == 2 ? (c & 1) : 0) * HC);
+            const uint32_t d = tmem + (uint32_t)(p.col_acc + ab * N2);
+            MF_TL(3, c);
+            if (p.resident) {
+                if (c < NCH)
+                    for (int kb = 0; kb < 2; ++kb) MF_WAIT(3, bar(B_W2FULL + j * 2 + kb), 0u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t base = sW2 + (uint32_t)j * 2u * ST2;
+                    issue2(base, 0, a_hi, a_lo, d, j == 0);
+                    issue2(base + ST2, 1, a_hi, a_lo, d, j == 0);
+                    umma_commit(bar(B_RFREE + (c & 1)));
+                    if (p.nl == 1) umma_commit(bar(B_LFREE));
+                    if (j + 1 == NCH) umma_commit(bar(B_ACCFULL + ab));
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    MF_WAIT(3, bar(B_W2FULL + wslot), wphase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t base = sW + (uint32_t)j * CHUNK;
-#pragma unroll
-                        for (int kb = 0; kb < NKB1; ++kb) issue1(base + (uint32_t)kb * ST1_BYTES, kb, a_hi, a_lo, d);
-                        umma_commit(bar(B_RFULL + (c & 1)));
-                        if (j + 1 == NCH) umma_commit(bar(B_A1FREE + a));
+                        issue2(sW2 + wslot * ST2, kb, a_hi, a_lo, d, j == 0);
+                        umma_commit(bar(B_W2FREE + wslot));
+                        if (kb == 1) {
+                            umma_commit(bar(B_RFREE + (c & 1)));
+                            if (p.nl == 1) umma_commit(bar(B_LFREE));
+                            if (j + 1 == NCH) umma_commit(bar(B_ACCFULL + ab));
+                        }
                     }
                     __syncwarp();
-                } else {
-#pragma unroll
-                    for (int kb = 0; kb < NKB1; ++kb) {
-                        MF_WAIT(3, bar(B_WFULL + wslot), wphase);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue1(sW + wslot * p.slot_bytes, kb, a_hi, a_lo, d);
-                            umma_commit(bar(B_WFREE + wslot));
-                            if (kb + 1 == NKB1) {
-                                umma_commit(bar(B_RFULL + (c & 1)));
-                                if (j + 1 == NCH) umma_commit(bar(B_A1FREE + a));
-                            }
-                        }
-                        __syncwarp();
-                        if (++wslot == (uint32_t)p.ns) { wslot = 0; wphase ^= 1; }
-                    }
+                    if (++wslot == (uint32_t)p.ns2) { wslot = 0; wphase ^= 1; }
                 }
-                MF_TL(2, c);
-            },
-            [&](int c) {                                                           // G2(c): ACC2 += GELU chunk * W2[:, chunk]^T
-                const int t = c / NCH, j = c % NCH, ab = p.nacc == 2 ? t & 1 : 0;
-                MF_WAIT(1, bar(B_HFULL + (c & 1)), (uint32_t)((c >> 1) & 1));
-                if (j == 0) MF_WAIT(2, bar(B_ACCFREE + ab), (uint32_t)(((p.nacc == 2 ? t >> 1 : t) & 1) ^ 1));
-                const uint32_t a_hi = tmem + (uint32_t)(p.col_r + (c & 1) * HC);
-                const uint32_t a_lo = tmem + (uint32_t)(p.col_l + (p.nl == 2 ? (c & 1) : 0) * HC);
-                const uint32_t d = tmem + (uint32_t)(p.col_acc + ab * N2);
-                MF_TL(3, c);
-                if (p.resident) {
-                    if (c < NCH)
-                        for (int kb = 0; kb < 2; ++kb) MF_WAIT(3, bar(B_WFULL + j * (NKB1 + 2) + NKB1 + kb), 0u);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t base = sW + (uint32_t)j * CHUNK + G::FC1;
-                        issue2(base, 0, a_hi, a_lo, d, j == 0);
-                        issue2(base + ST2, 1, a_hi, a_lo, d, j == 0);
-                        if (p.nl == 1) umma_commit(bar(B_LFREE));
-                        if (j + 1 == NCH) umma_commit(bar(B_ACCFULL + ab));
-                    }
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int kb = 0; kb < 2; ++kb) {
-                        MF_WAIT(3, bar(B_WFULL + wslot), wphase);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue2(sW + wslot * p.slot_bytes, kb, a_hi, a_lo, d, j == 0);
-                            umma_commit(bar(B_WFREE + wslot));
-                            if (kb == 1) {
-                                if (p.nl == 1) umma_commit(bar(B_LFREE));
-                                if (j + 1 == NCH) umma_commit(bar(B_ACCFULL + ab));
-                            }
-                        }
-                        __syncwarp();
-                        if (++wslot == (uint32_t)p.ns) { wslot = 0; wphase ^= 1; }
-                    }
-                }
-                MF_TL(4, c);
-            });
+            }
+            MF_TL(4, c);
+        }
     } else if (warp >= LN_BASE && warp < LN_BASE + 4) {
         // ================================================================================ LayerNorm -> A1 (TMEM)
         const int q = warp & 3, r = q * 32 + lane;
@@ -584,7 +586,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
         // marker) | 14 CTAs | 15 signature
         const unsigned long long total_clk = (unsigned long long)(clock64() - tr_start);
         unsigned long long* t = p.trace;
-        if (warp == W_MMA && lane == 0) { atomicAdd(t + 0, total_clk); for (int i = 0; i < 4; ++i) atomicAdd(t + 1 + i, (unsigned long long)tr[i]); atomicAdd(t + 14, 1ull); }
+        // mma columns: 1 = issuer 1's wait for A1, 2 / 3 = issuer 2's waits for the GELU chunk / the ACC2 release, 4 = both issuers' weight waits
+        if (warp == W_MMA2 && lane == 0) { atomicAdd(t + 0, total_clk); atomicAdd(t + 2, (unsigned long long)tr[1]); atomicAdd(t + 3, (unsigned long long)tr[2]); atomicAdd(t + 4, (unsigned long long)tr[3]); atomicAdd(t + 14, 1ull); }
+        if (warp == W_MMA1 && lane == 0) { atomicAdd(t + 1, (unsigned long long)tr[0]); atomicAdd(t + 4, (unsigned long long)tr[3]); }
         if (warp == LN_BASE && lane == 0) { atomicAdd(t + 5, total_clk); atomicAdd(t + 6, (unsigned long long)tr[0]); atomicAdd(t + 7, (unsigned long long)tr[1]); }
         if (warp == GELU_BASE && lane == 0) { atomicAdd(t + 8, total_clk); atomicAdd(t + 9, (unsigned long long)tr[0]); atomicAdd(t + 10, (unsigned long long)tr[1]); }
         if (warp == OUT_BASE && lane == 0) { atomicAdd(t + 11, total_clk); atomicAdd(t + 12, (unsigned long long)tr[0]); }
@@ -654,7 +658,7 @@ cudaError_t launch(cudaStream_t st, const Weights& w, float* x, long long M, flo
         return cudaErrorInvalidValue;
     Params p;
     p.C = pl.C; p.ld = pl.ld; p.Kp16 = pl.Kp16; p.ksteps1 = pl.ksteps1; p.nkb1 = pl.nkb1; p.nch = pl.nch; p.N2 = pl.N2;
-    p.nx = pl.nx; p.na1 = pl.na1; p.nl = pl.nl; p.nacc = pl.nacc; p.resident = pl.resident; p.ns = pl.ns;
+    p.nx = pl.nx; p.na1 = pl.na1; p.nl = pl.nl; p.nacc = pl.nacc; p.resident = pl.resident; p.ns1 = pl.ns1; p.ns2 = pl.ns2;
     p.nboxf = pl.nboxf; p.rem = pl.rem;
     p.st2_bytes = pl.st2_bytes; p.slot_bytes = pl.slot_bytes; p.chunk_bytes = pl.chunk_bytes; p.xslot_bytes = pl.xslot_bytes;
     p.col_a1 = pl.col_a1; p.col_r = pl.col_r; p.col_l = pl.col_l; p.col_acc = pl.col_acc;

@@ -45,9 +45,14 @@ constexpr int HC = 64;                  // hidden columns per chunk = UMMA N of 
 #endif
 constexpr int LN_BASE = 0, OUT_BASE = 4, GELU_BASE = 8, GELU_WARPS = ESCB_MF_GELU_WARPS;   // 8 or 16: 32 or 16 hidden columns per thread and chunk
 constexpr int GELU_COLS = HC / (GELU_WARPS / 4);
-constexpr int W_XLOAD = GELU_BASE + GELU_WARPS, W_WLOAD = W_XLOAD + 1, W_ALLOC = W_XLOAD + 2, W_MMA = W_XLOAD + 3;
-constexpr int WARPS = W_MMA + 1, THREADS = WARPS * 32;
-constexpr int MAX_WST = 16;             // weight stage barriers (ring slots, or all stages of a tile when resident)
+// Two MMA-issuing warps: W_MMA1 issues the fc1 chunks (G1), W_MMA2 the fc2 partial products (G2).  tcgen05.mma issue is
+// nearly synchronous with the tensor pipe (the issuing thread stalls while its MMAs execute), so with ONE issuer the
+// per-op overhead (barrier probes, descriptor arithmetic, commits: ~1 kclk per chunk at C = 45) ran with the pipe idle;
+// with two, one warp's overhead hides behind the other's MMAs.  Each has its own weight loader warp and ring.
+constexpr int W_XLOAD = GELU_BASE + GELU_WARPS, W_WLOAD1 = W_XLOAD + 1, W_WLOAD2 = W_XLOAD + 2, W_MMA1 = W_XLOAD + 3, W_MMA2 = W_XLOAD + 4;
+constexpr int W_ALLOC = W_XLOAD;        // the x loader warp also allocates / frees tensor memory
+constexpr int WARPS = W_MMA2 + 1, THREADS = WARPS * 32;
+constexpr int MAX_WST = 8;              // weight stage barriers per layer (ring slots, or all stages of a tile when resident)
 constexpr int MAX_NX = 3;
 constexpr int BOX_BYTES = BM * 128;     // one 32-column box of the x tile: 128 rows x 128 bytes
 constexpr int ST1_BYTES = 2 * HC * 128; // fc1 stage: [hi | lo] images of 64 hidden rows x one 32-wide K block
@@ -62,12 +67,13 @@ constexpr int MAX_C = 96;
 // barrier indices
 constexpr int B_XFULL = 0, B_XFREE = B_XFULL + MAX_NX, B_A1FULL = B_XFREE + MAX_NX, B_A1FREE = B_A1FULL + 2,
               B_RFULL = B_A1FREE + 2, B_HFULL = B_RFULL + 2, B_LFREE = B_HFULL + 2, B_ACCFULL = B_LFREE + 1,
-              B_ACCFREE = B_ACCFULL + 2, B_WFULL = B_ACCFREE + 2, B_WFREE = B_WFULL + MAX_WST, NBARS = B_WFREE + MAX_WST;
+              B_ACCFREE = B_ACCFULL + 2, B_RFREE = B_ACCFREE + 2, B_W1FULL = B_RFREE + 2, B_W1FREE = B_W1FULL + MAX_WST,
+              B_W2FULL = B_W1FREE + MAX_WST, B_W2FREE = B_W2FULL + MAX_WST, NBARS = B_W2FREE + MAX_WST;
 
 // ---------------------------------------------------------------------------------------------------- host side
 struct Plan {                       // geometry of the fused kernel for one channel width (filled at pack time)
     int ok = 0;
-    int C, ld, Kp16, ksteps1, nkb1, nch, N2, nx, na1, nl, nacc, resident, ns, nboxf, rem;
+    int C, ld, Kp16, ksteps1, nkb1, nch, N2, nx, na1, nl, nacc, resident, ns1, ns2, nboxf, rem;
     unsigned st2_bytes, slot_bytes, chunk_bytes, xslot_bytes;
     int col_a1, col_r, col_l, col_acc;
     size_t smem_bytes;
@@ -106,26 +112,31 @@ inline Plan make_plan(int C, int hidden) {
     // shared memory: x slots | weights | barriers
     const size_t tail = NBARS * 8 + 64, budget = tc::SMEM_MAX - 1024;
     const size_t w_all = (size_t)pl.nch * pl.chunk_bytes;
+    const size_t fc1_chunk = pl.chunk_bytes - 2 * (size_t)pl.st2_bytes;
     pl.nx = 2;
-    pl.resident = (2 * (size_t)pl.xslot_bytes + w_all + tail <= budget && pl.nch * (pl.nkb1 + 2) <= MAX_WST) ? 1 : 0;
+    pl.resident = (2 * (size_t)pl.xslot_bytes + w_all + tail <= budget && pl.nch * pl.nkb1 <= MAX_WST && pl.nch * 2 <= MAX_WST) ? 1 : 0;
     if (pl.resident) {
-        pl.ns = pl.nch * (pl.nkb1 + 2);
+        pl.ns1 = pl.nch * pl.nkb1;
+        pl.ns2 = pl.nch * 2;
         if (3 * (size_t)pl.xslot_bytes + w_all + tail <= budget) pl.nx = 3;
         pl.smem_bytes = 1024 + (size_t)pl.nx * pl.xslot_bytes + w_all + tail;
     } else {
-        size_t left = budget - tail - 2 * (size_t)pl.xslot_bytes;
-        int ns = (int)(left / pl.slot_bytes);
-        if (ns > MAX_WST) ns = MAX_WST;
-        if (ns < pl.nkb1 + 2) return pl;                  // one chunk's G1 + G2 stages must fit the ring
-        // a third x slot if it still leaves a two-chunk ring
-        if (ns - (int)((pl.xslot_bytes + pl.slot_bytes - 1) / pl.slot_bytes) >= 2 * (pl.nkb1 + 2)) {
-            pl.nx = 3;
-            left -= pl.xslot_bytes;
-            ns = (int)(left / pl.slot_bytes);
-            if (ns > MAX_WST) ns = MAX_WST;
+        // two rings (fc1 slots of ST1_BYTES, fc2 slots of st2_bytes): at least one chunk of each, then grow them in turn
+        const size_t left = budget - tail - 2 * (size_t)pl.xslot_bytes;
+        int n1 = pl.nkb1, n2 = 2;
+        if ((size_t)n1 * ST1_BYTES + (size_t)n2 * pl.st2_bytes > left) return pl;
+        for (;;) {
+            const size_t used = (size_t)n1 * ST1_BYTES + (size_t)n2 * pl.st2_bytes;
+            const bool can1 = n1 < MAX_WST && n1 < 2 * pl.nkb1 + 1 && used + ST1_BYTES <= left;
+            const bool can2 = n2 < MAX_WST && n2 < 4 && used + pl.st2_bytes <= left;
+            if (can1 && (n1 - pl.nkb1 <= (n2 - 2) || !can2)) ++n1;
+            else if (can2) ++n2;
+            else break;
         }
-        pl.ns = ns;
-        pl.smem_bytes = 1024 + (size_t)pl.nx * pl.xslot_bytes + (size_t)ns * pl.slot_bytes + tail;
+        pl.ns1 = n1;
+        pl.ns2 = n2;
+        (void)fc1_chunk;
+        pl.smem_bytes = 1024 + (size_t)pl.nx * pl.xslot_bytes + (size_t)n1 * ST1_BYTES + (size_t)n2 * pl.st2_bytes + tail;
     }
     pl.ok = 1;
     return pl;
