@@ -15,6 +15,11 @@ import json
 import sys
 
 RULES = [   # (substring of the demangled kernel name, class); first match wins
+    ("mlp_fused_kernel", "mlp_fused"),
+    ("pvq_stream_kernel", "pvq_stream_fused"),
+    ("rvq_chain_kernel", "codebook_argmin"),
+    ("rvq_gather_kernel", "layout"),
+    ("code_histogram_kernel", "layout"),
     ("EpiAttn<", "qkv_attention_fused"),
     ("AWindow, EpiRows", "qkv_gemm"),
     ("window_attn_kernel", "window_attention"),
@@ -57,6 +62,13 @@ def main(src, dst):
         elif r[12].startswith("gpu__time"):
             v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
         d[r[12]] = v
+    # the capture may hold warm-up steps: keep the LAST step (every encode starts with the STFT GEMM)
+    ids = list(per_launch)
+    starts = [i for i in ids if "AStftFrames" in per_launch[i]["name"]]
+    if len(starts) > 1:
+        for i in ids:
+            if i < starts[-1]:
+                del per_launch[i]
     out = collections.OrderedDict()
     pending = None                                     # LayerNorm statistics launch waiting for its GEMM
     for lid, d in per_launch.items():
@@ -78,13 +90,15 @@ def main(src, dst):
             e["dram_write_bytes"] += pending[1]
             e["time_us"] += pending[2]
             pending = None
+    total_bytes = sum(e["dram_read_bytes"] + e["dram_write_bytes"] for e in out.values())
     for e in out.values():
         e["dram_bytes_per_launch"] = (e["dram_read_bytes"] + e["dram_write_bytes"]) / max(e["launches"], 1)
     tot = sum(e["time_us"] for e in out.values()) or 1.0
     for e in out.values():
         e["share_of_step"] = round(e["time_us"] / tot, 4)
     json.dump({"source": src, "note": "one encode+decode step, ESC-Base, 36 x 3 s clips; ncu serialises launches and "
-               "runs them cold-cache, so shares (not absolute times) are comparable with bench.py", "classes": out},
+               "runs them cold-cache, so shares (not absolute times) are comparable with bench.py",
+               "launches_in_step": sum(e["launches"] for e in out.values()), "dram_bytes_per_step": total_bytes, "classes": out},
               open(dst, "w"), indent=1)
     for k, e in sorted(out.items(), key=lambda kv: -kv[1]["time_us"]):
         print(f"{k:24s} {e['launches']:4d} launches {e['time_us']:9.1f} us  share {e['share_of_step']:.3f}  "
