@@ -289,6 +289,53 @@ def rvq_microbench(model, dev, flush, peaks, iters=20):
                             "bound": "hbm", "api": "escb_pvq_stream: one fused launch per stream step (enc, dec -> codes, dec_refine)"}}
 
 
+def small_batch_latency(model, dev, batch=1, iters=50):
+    """Latency of encode + decode of `batch` 3 s clips: the ~190 launches issued eagerly, and
+    the same launches captured once in a CUDA graph and replayed (the stream chain is sequential, so at B=1 the step is
+    launch-latency bound)."""
+    import torch
+    from escb200.synthetic import synth_audio
+    x = synth_audio(batch, CLIP_SAMPLES, seed=77).to(dev)
+
+    def step():
+        codes, fs = model.encode(x, 6)
+        return codes, model.decode(codes, fs)
+    for _ in range(3):
+        ref_codes, ref_audio = step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    eager_ms = e0.elapsed_time(e1) / iters
+    out = {"batch": batch, "eager_ms": eager_ms, "eager_clips_per_s": batch / (eager_ms * 1e-3)}
+    try:
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            step()
+            with torch.cuda.graph(g, stream=s):
+                g_codes, g_audio = step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        same = bool(torch.equal(g_codes, ref_codes) and torch.equal(g_audio, ref_audio))
+        e0.record()
+        for _ in range(iters):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        graph_ms = e0.elapsed_time(e1) / iters
+        out.update({"graph_ms": graph_ms, "graph_clips_per_s": batch / (graph_ms * 1e-3), "graph_equals_eager": same,
+                    "how": "torch.cuda.graph around ESC.encode + ESC.decode (the C-ABI calls launch on the capturing stream)"})
+    except Exception as e:                               # capture is an optimisation, not part of the contract
+        out["graph_error"] = repr(e)[:200]
+    return out
+
+
 def incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, steps):
     """The reference itself in eager PyTorch ON THIS GPU (fp32, TF32 off for matmul and cuDNN): the practical incumbent,
     since the reference has no native kernels - plus the parity noise floor reference-CPU vs reference-GPU."""
@@ -557,7 +604,7 @@ def main_b200(args):
         by = sum(prof[n]["bytes"] for n in names if n in prof)
         return {"achieved": by / max(ms, 1e-9) / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": by / max(ms, 1e-9) / 1e6 / peaks["hbm"], "ms_per_step": ms / args.steps}
-    rvq = {"in_step_b36": {"argmin_only": rvq_entry(["codebook_argmin"]),
+    rvq = {"in_step_b36": {"argmin_only": rvq_entry(["codebook_argmin"]) if prof.get("codebook_argmin", {}).get("launches") else None,
                            "stream_step": rvq_entry(["pvq_down_gemm", "codebook_argmin", "pvq_up_gemm", "pvq_stream_fused"])},
            "note": "argmin-only is FMA-issue bound by construction (460 flop/B, SURVEY 8d); the stream step is the HBM-bound one"}
     extra = {}
@@ -574,6 +621,9 @@ def main_b200(args):
             if ms is not None:
                 sweep[str(s)] = {"kbps": 1.5 * s, "value": B * k / (ms * 1e-3), "ms_per_step": ms / k}
         extra["num_streams_sweep"] = {"unit": UNIT, "batch": B, "per_num_streams": sweep}
+        # ---- small-batch latency: one clip, eager launches vs CUDA graph replay
+        if N == 1:
+            extra["latency_b1"] = small_batch_latency(model, dev, 1)
         # ---- the reference in eager PyTorch on this GPU + parity noise floor
         my_codes, my_audio = step_device(x_dev, S, gather=False)
         extra["incumbent"] = incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, args.steps)
