@@ -496,8 +496,8 @@ static void pack_layer(Packer& P, int li) {
 }
 
 // normalised / transposed / raw forms of one codebook (codebook.py:32-40), appended to the three vectors
-static void pack_codebook(const std::vector<float>& e, int K, int dd, std::vector<float>& raw, std::vector<float>& cbt,
-                          std::vector<float>& cn) {
+static void pack_codebook(const std::vector<float>& e, int K, int dd, bool l2norm, std::vector<float>& raw,
+                          std::vector<float>& cbt, std::vector<float>& cn) {
     const size_t r0 = raw.size(), t0 = cbt.size(), n0 = cn.size();
     raw.resize(r0 + (size_t)K * dd);
     cbt.resize(t0 + (size_t)K * dd);
@@ -505,7 +505,7 @@ static void pack_codebook(const std::vector<float>& e, int K, int dd, std::vecto
     for (int c = 0; c < K; ++c) {
         float ss = 0.f;
         for (int j = 0; j < dd; ++j) { const float v = e[(size_t)c * dd + j]; ss = fmaf(v, v, ss); }
-        const float den = fmaxf(sqrtf(ss), 1e-12f);
+        const float den = l2norm ? fmaxf(sqrtf(ss), 1e-12f) : 1.0f;     // l2norm=False: the table itself (codebook.py:31-40)
         float s2 = 0.f;
         for (int j = 0; j < dd; ++j) {
             const float v = e[(size_t)c * dd + j];
@@ -526,7 +526,7 @@ static void pack_projections(Packer& P, QuantW& qw, int C, int Hq, int dd, int K
     int vq[3], start[3];
     split_dims(frame, 3, vq);
     start[0] = 0; start[1] = vq[0]; start[2] = vq[0] + vq[1];
-    qw.in_dim = C; qw.in_freq = Hq; qw.d = dd; qw.frame_dim = frame; qw.ncodes = K;
+    qw.in_dim = C; qw.in_freq = Hq; qw.d = dd; qw.frame_dim = frame; qw.ncodes = K; qw.l2norm = P.h->cfg.l2norm ? 1 : 0;
     std::vector<float> down, up;
     Packer::init_gemm(qw.down, 3 * dd, frame, down);
     Packer::init_gemm(qw.up, frame, 3 * dd, up);
@@ -581,7 +581,7 @@ static void pack_quant(Packer& P, int q) {
                      [&](int g) { return p + ".up_projs." + std::to_string(g) + ".weight"; });
     // codebooks: raw, L2-normalised (F.normalize, eps 1e-12) and squared norms of the normalised rows (codebook.py:32-40)
     std::vector<float> raw, cbt, cn;
-    for (int g = 0; g < 3; ++g) pack_codebook(P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight"), K, d.d, raw, cbt, cn);
+    for (int g = 0; g < 3; ++g) pack_codebook(P.w(p + ".vqs." + std::to_string(g) + ".embedding.weight"), K, d.d, h->cfg.l2norm != 0, raw, cbt, cn);
     P.put(&qw.raw, raw);
     P.put(&qw.cbt, cbt);
     P.put(&qw.cnorm, cn);
@@ -601,7 +601,7 @@ static void pack_rvq(Packer& P) {
     std::vector<float> raw, cbt, cn;
     for (int g = 0; g < 3; ++g)
         for (int i = 0; i < S; ++i)
-            pack_codebook(P.w("quantizers.vqs." + std::to_string(g) + ".vqs." + std::to_string(i) + ".embedding.weight"), K, d.d, raw, cbt, cn);
+            pack_codebook(P.w("quantizers.vqs." + std::to_string(g) + ".vqs." + std::to_string(i) + ".embedding.weight"), K, d.d, h->cfg.l2norm != 0, raw, cbt, cn);
     P.put(&w.raw, raw);
     P.put(&w.cbt, cbt);
     P.put(&w.cnorm, cn);
@@ -1014,7 +1014,6 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (c.window_size != 4) return fail(ESCB_EINVAL, "window_size must be 4");
     if (c.group_size != 3) return fail(ESCB_EINVAL, "group_size must be 3");
     if (c.overlap != 2) return fail(ESCB_EINVAL, "overlap must be 2");
-    if (!c.l2norm) return fail(ESCB_EINVAL, "l2norm=False is not supported");
     if (c.patch_freq < 1 || c.patch_time < 1 || 2 * c.patch_freq * c.patch_time > kEmbedMaxK)
         return fail(ESCB_EINVAL, "unsupported patch size (%d, %d)", c.patch_freq, c.patch_time);
     if (c.in_freq < 2 || c.in_freq % c.patch_freq) return fail(ESCB_EINVAL, "in_freq must be a multiple of patch_freq");
@@ -1216,6 +1215,32 @@ int escb_forward(escb_handle* h, const float* audio, int32_t B, int64_t Ls, int3
     } else run_csrvq_forward(c, S, codes ? (long long*)codes : c.wk.codes, vq_loss);
     run_backend(c, audio_out, recon_feat);
     return finish(c, "escb_forward");
+}
+
+// forward(eval) from a precomputed spectrum (x_feat of ESC.forward, codecs.py:33-34): the STFT is skipped.
+int escb_forward_feat(escb_handle* h, const float* planes, int32_t B, int32_t T, int32_t S, int64_t* codes, float* audio_out,
+                      float* recon_feat, float* vq_loss, void* ws, size_t ws_bytes, void* stream) {
+    if (int e = check_ready(h)) return e;
+    if (!planes) return fail(ESCB_EINVAL, "null argument");
+    if (S < 1 || S > max_streams_of(h)) return fail(ESCB_EINVAL, "num_streams must be in [1, %d]", max_streams_of(h));
+    if (T < h->pt) return fail(ESCB_EINVAL, "too few frames");
+    const int W = (T - h->pt) / h->pt + 1;
+    if (W <= 0 || W % h->cfg.overlap) return fail(ESCB_EINVAL, "Time dimension must be multiple of overlap (W=%d, overlap=%d)", W, h->cfg.overlap);
+    Ctx c;
+    if (int e = begin(h, c, B, W, T, WK_ENC | WK_DEC, ws, ws_bytes, stream)) return e;
+    op_transpose(c.L, planes, c.wk.Sf, B, 2 * h->F, T);                 // [B, 2F, T] planes -> frame-major [B, T, 2F]
+    run_encoder(c, T);
+    if (vq_loss) {
+        const cudaError_t e = cudaMemsetAsync(vq_loss, 0, (size_t)B * sizeof(float), c.L.st);
+        if (e != cudaSuccess && c.L.err == cudaSuccess) c.L.err = e;
+    }
+    if (h->cfg.num_rvqs > 0) {
+        run_rvq_quantize(c, S, codes ? (long long*)codes : c.wk.codes, c.wk.zq, vq_loss ? c.wk.se : nullptr);
+        if (vq_loss) op_rvq_loss(c.L, c.wk.se, B, W / 2, h->rvq.q.d, vq_loss);
+        run_rvq_decoder(c, c.wk.zq);
+    } else run_csrvq_forward(c, S, codes ? (long long*)codes : c.wk.codes, vq_loss);
+    run_backend(c, audio_out, recon_feat);
+    return finish(c, "escb_forward_feat");
 }
 
 // Host-buffer variants: H2D, run, D2H, synchronise.

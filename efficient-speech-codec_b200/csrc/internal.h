@@ -38,7 +38,7 @@ struct LayerW {
 };
 
 struct QuantW {
-    int in_dim, in_freq, d, frame_dim, ncodes;
+    int in_dim, in_freq, d, frame_dim, ncodes, l2norm;
     GemmWeight down;                                 // K = frame_dim in (h,o,c) order, N = 3d (block structured)
     GemmWeight down_g[3];                            // per group: K = frame_dim / 3 (its (o,c) third of every h run), N = d
     int run;                                         // 2C/3 when the groups are equal (o,c) thirds (else 0: stacked path only)

@@ -146,7 +146,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int d_stride, const float* __restrict__ cbt,
                        const float* __restrict__ cnorm, const int ncodes, const long long rows,
-                       long long* __restrict__ out, const int T, const long long bstride) {
+                       long long* __restrict__ out, const int T, const long long bstride, const int l2norm) {
     __shared__ __align__(16) float zs[D][kArgminRows];        // 2 * z_hat, transposed
     __shared__ float zzs[kArgminRows];
     __shared__ __align__(16) float cbs[D][kArgminChunk];
@@ -167,7 +167,7 @@ codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int d_s
 #pragma unroll
             for (int k = 0; k < D; ++k) zn[k] = 0.f;
         }
-        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+        const float denom = l2norm ? fmaxf(sqrtf(ss), 1e-12f) : 1.0f;      // l2norm=False: plain squared distance (codebook.py:31-40)
         float zz = 0.f;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -478,6 +478,7 @@ struct PvqStreamArgs {
     const float* cnorm;         // [3][ncodes]
     const float* raw;           // [3][ncodes][d]
     int* bad;                   // host-mapped latch for out-of-range codes given to the decode-only form
+    int l2norm;                 // 1: both sides L2-normalised (the shipped configs); 0: plain squared distance
     int ncodes, Hq, W, C, run, Kg, T;
     long long rows;             // B * T
     FastDiv drun4;              // by run / 4 (float4 groups per frequency run)
@@ -630,7 +631,7 @@ pvq_stream_kernel(const PvqStreamArgs a) {
             float ss = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) { zn[k] = zs[tid][k]; ss = fmaf(zn[k], zn[k], ss); }
-            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+            const float denom = a.l2norm ? fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
             float zz = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
@@ -762,7 +763,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 rvq_chain_kernel(const float* __restrict__ ze, const int ldz, const float* __restrict__ cbt, const float* __restrict__ cnorm,
                  const float* __restrict__ raw, const int ncodes, const int Stot, const int S, const long long rows,
-                 long long* __restrict__ codes, const int T, float* __restrict__ zq, float* __restrict__ se) {
+                 long long* __restrict__ codes, const int T, float* __restrict__ zq, float* __restrict__ se, const int l2norm) {
     __shared__ float res[kArgminRows][D + 1];                  // running residual
     __shared__ float zqa[kArgminRows][D + 1];
     __shared__ float sea[kArgminRows];
@@ -790,7 +791,7 @@ rvq_chain_kernel(const float* __restrict__ ze, const int ldz, const float* __res
             float ss = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) { zn[k] = res[tid][k]; ss = fmaf(zn[k], zn[k], ss); }
-            const float denom = fmaxf(sqrtf(ss), 1e-12f);
+            const float denom = l2norm ? fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
             float zz = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {

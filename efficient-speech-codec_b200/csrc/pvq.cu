@@ -45,7 +45,7 @@ static cudaError_t launch_argmin(cudaStream_t st, const QuantW& q, int g_first, 
     dim3 grid((unsigned)((rows + kArgminRows - 1) / kArgminRows), (unsigned)groups);
     codebook_argmin_kernel<D><<<grid, 256, 0, st>>>(ze, ldz, q.d, q.cbt + (long long)g_first * q.ncodes * q.d,
                                                     q.cnorm + (long long)g_first * q.ncodes, q.ncodes, rows, out, T,
-                                                    bstride);
+                                                    bstride, q.l2norm);
     return cudaGetLastError();
 }
 
@@ -130,6 +130,7 @@ bool op_pvq_stream(Launcher& L, const QuantW& q, const float* enc, const float* 
     a.lgH = -1;
     for (int l = 0; l < 16; ++l) if ((1 << l) == q.in_freq) a.lgH = l;
     a.bad = L.code_err;
+    a.l2norm = q.l2norm;
     const double M = (double)a.rows, fd = q.frame_dim;
     if (enc) L.begin(OP_PVQ_STREAM, 2.0 * M * (fd * q.d * (out ? 2.0 : 1.0) + 3.0 * q.ncodes * q.d),
                      4.0 * M * fd * ((dec ? 2.0 : 1.0) + (out ? 1.0 : 0.0)) + 24.0 * M);
@@ -153,7 +154,7 @@ void op_rvq_chain(Launcher& L, const RvqW& w, const float* ze, int ldz, long lon
     dim3 grid((unsigned)((rows + kArgminRows - 1) / kArgminRows), 3);
     cudaError_t e = cudaErrorInvalidValue;
     switch (q.d) {
-#define X(n) case n: rvq_chain_kernel<n><<<grid, 256, 0, L.st>>>(ze, ldz, w.cbt, w.cnorm, w.raw, q.ncodes, w.S, S, rows, codes, T, zq, se); e = cudaGetLastError(); break;
+#define X(n) case n: rvq_chain_kernel<n><<<grid, 256, 0, L.st>>>(ze, ldz, w.cbt, w.cnorm, w.raw, q.ncodes, w.S, S, rows, codes, T, zq, se, q.l2norm); e = cudaGetLastError(); break;
         ESCB_STREAM_DS(X)
 #undef X
         default: break;

@@ -254,7 +254,7 @@ class ESC(nn.Module):
             raise RuntimeError("esc-b200 implements the inference path only: call model.eval() first "
                                "(training stays with the reference, SURVEY.md section 8f)")
         if x_feat is not None:
-            raise NotImplementedError("a precomputed x_feat is a training-loop input; pass x_feat=None")
+            return self._forward_from_feat(x, x_feat, int(num_streams))
         if x.dim() != 2:
             raise ValueError("x must have shape (Bs, L)")
         B, Ls = x.shape
@@ -279,6 +279,33 @@ class ESC(nn.Module):
         out = {"cm_loss": loss, "cb_loss": loss.clone(), "raw_audio": x, "recon_audio": audio, "raw_feat": raw,
                "recon_feat": rec, "codes": codes}
         if not x.is_cuda:
+            out = {k: (v.cpu() if k != "raw_audio" else v) for k, v in out.items()}
+        return out
+
+    def _forward_from_feat(self, x, x_feat, S):
+        """``forward`` with a precomputed complex STFT ``x_feat`` [Bs, F, T, 2] (codecs.py:33-34): no STFT is run."""
+        if x_feat.dim() != 4 or x_feat.shape[1] != self.spec.in_freq or x_feat.shape[3] != 2:
+            raise ValueError("x_feat must have shape (Bs, in_freq, T, 2)")
+        B, F, T, _ = x_feat.shape
+        pt = self.spec.patch_size[1]
+        W = (T - pt) // pt + 1
+        if W <= 0 or W % self.spec.overlap:
+            raise AssertionError("Time dimension must be multiple of overlap")
+        dev = self._exec_device(x_feat)
+        h = self._handle(dev)
+        with torch.cuda.device(dev), torch.no_grad():
+            planes = x_feat.detach().to(dev).permute(0, 3, 1, 2).contiguous().float()          # "b h w c -> b c h w"
+            codes = torch.empty((B, S, self.spec.group_size, W // self.spec.overlap), dtype=torch.int64, device=dev)
+            audio = torch.empty((B, h.decoded_samples(W)), dtype=torch.float32, device=dev)
+            rec = torch.empty((B, 2, F, pt * W), dtype=torch.float32, device=dev)
+            loss = torch.empty((B,), dtype=torch.float32, device=dev)
+            ws = self._ws(dev, h.workspace_bytes(B, W))
+            native.check(native.lib().escb_forward_feat(h.ptr, native.ptr(planes), B, T, S, native.ptr(codes), native.ptr(audio),
+                                                        native.ptr(rec), native.ptr(loss), native.ptr(ws), ws.numel(),
+                                                        self._stream(dev)))
+        out = {"cm_loss": loss, "cb_loss": loss.clone(), "raw_audio": x, "recon_audio": audio, "raw_feat": planes,
+               "recon_feat": rec, "codes": codes}
+        if not x_feat.is_cuda:
             out = {k: (v.cpu() if k != "raw_audio" else v) for k, v in out.items()}
         return out
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "escb_workspace_bytes", "escb_encode", "escb_decode", "escb_forward", "escb_encode_host", "escb_decode_host",
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
-    "escb_poll_error", "escb_code_histogram", "escb_pvq_stream",
+    "escb_poll_error", "escb_code_histogram", "escb_pvq_stream", "escb_forward_feat",
 ]
 ESCB_NUM_OPS = 20
 
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         "escb_encode": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, sz, vp]),
         "escb_decode": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]),
         "escb_forward": (C.c_int, [vp, vp, i32, i64, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
+        "escb_forward_feat": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
         "escb_encode_host": (C.c_int, [vp, vp, i32, i64, i32, vp, vp]),
         "escb_decode_host": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
         "escb_stft": (C.c_int, [vp, vp, i32, i64, vp, vp, sz, vp]),

@@ -139,6 +139,12 @@ ESCB_API int escb_forward(escb_handle* h, const float* audio_dev, int32_t batch,
                  int64_t* codes_dev, float* audio_out_dev, float* raw_feat_dev, float* recon_feat_dev,
                  float* vq_loss_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The same pass from a precomputed spectrum: ESC.forward(x, x_feat, ...) with x_feat given (esc/models/codecs.py:33-34,
+ * after its rearrange to [batch, 2, in_freq, frames]); the STFT is skipped, W = (frames - patch_time) / patch_time + 1. */
+ESCB_API int escb_forward_feat(escb_handle* h, const float* planes_dev, int32_t batch, int32_t frames, int32_t num_streams,
+                      int64_t* codes_dev, float* audio_out_dev, float* recon_feat_dev, float* vq_loss_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Host-buffer variants: the same calls for callers that hold host memory (scripts/compress.py:19-35 runs the
  * codec on a wav it just read).  They allocate device scratch internally, copy in, run, copy out and
  * synchronise `stream` before returning.  Host buffers should be pinned for full PCIe bandwidth. */

@@ -348,6 +348,37 @@ def test_eval_sweep_all_bitrates(base0, tmp_path):
     assert float(ec._counts.sum()) == 6 * 3 * 4 * 150
 
 
+def test_forward_from_precomputed_feat(base0):
+    """ESC.forward(x, x_feat, s) with x_feat [Bs, F, T, 2] given (codecs.py:33-34) skips the STFT and matches forward(x)."""
+    x = synth_audio(2, 16000, seed=61).cuda()
+    a = base0(x, None, 5)
+    x_feat = a["raw_feat"].permute(0, 2, 3, 1).contiguous()            # [B, 2, F, T] -> [B, F, T, 2]
+    b = base0(x, x_feat, 5)
+    assert torch.equal(b["codes"], a["codes"])
+    assert torch.equal(b["recon_audio"], a["recon_audio"])
+    assert torch.equal(b["cm_loss"], a["cm_loss"]) and torch.equal(b["raw_feat"], a["raw_feat"])
+    with pytest.raises(ValueError):
+        base0(x, x_feat[:, :100], 5)
+
+
+def test_l2norm_false_matches_oracle():
+    """l2norm=False (plain squared-distance argmin, codebook.py:31-40): codes and audio against the oracle."""
+    cfg = dict(BASE, l2norm=False)
+    m, _ = make_native(cfg, 14)
+    o = make_oracle(cfg, 14)[0]
+    x = synth_audio(2, 16000, seed=15)
+    codes, fs = m.encode(x.cuda(), 6)
+    ref, _ = o.encode(x, 6)
+    assert torch.equal(codes.cpu(), ref)
+    assert maxabs(m.decode(codes, fs).cpu(), o.decode(ref, fs)) <= AUDIO_TOL
+    u = Unit(m)
+    g = torch.Generator().manual_seed(3)
+    for q, d in enumerate(o.cfg.codebook_dims):
+        z = torch.randn(512, d, generator=g)
+        from oracle.esc_oracle import codebook_argmin
+        assert torch.equal(u.argmin(q, 1, z), codebook_argmin(z[None], o.sd[f"quantizers.{q}.vqs.1.embedding.weight"], False)[0])
+
+
 def test_host_buffer_path_equals_device_path(base0):
     """escb_encode_host / escb_decode_host (CPU tensors in, CPU tensors out) give the same bits."""
     x = synth_audio(3, 16000, seed=31)
