@@ -284,6 +284,10 @@ struct TcWeight {
     int N, K, BN, nsub, ntn, nkb;     // ntn output tiles of nsub sub-tiles of BN columns (tc::choose_tiling)
     int resident;       // the whole n-tile (nkb K blocks) stays in shared memory for the life of a CTA
     int wide;           // tiled for the 16-epilogue-warp role split (tc::Roles<4>)
+    // Accumulator split (tc_gemm.cuh "accumulator split"): the hi*hi products of K block kb go to MAIN accumulator
+    // kb % nmain; corr = 1 sends the lo*hi + hi*lo corrections to an accumulator of their own.  A sub-tile's region is
+    // (nmain + corr) * BN TMEM columns [main 0 | ... | corr], summed by the epilogue.  nmain = 1, corr = 0: one accumulator.
+    int nmain, corr;
 };
 
 struct GemmWeight {     // Wt [Kpad][ldw] row-major, zero padded; bias may be null

@@ -33,6 +33,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -217,6 +218,20 @@ __device__ __forceinline__ void tmem_ld_wait(float* v) {
     for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]) :: "memory");
 }
 
+// Sum of the `accs` accumulators of a split region (N columns of each, BN columns apart): mains in order, the
+// correction accumulator last.  The first load is left in flight when accs == 1 (the caller waits either way).
+template <int N>
+__device__ __forceinline__ void tmem_ld_acc(uint32_t taddr, float* v, int accs, int BN) {
+    tmem_ld_cols<N>(taddr, v);
+    for (int a = 1; a < accs; ++a) {
+        float u[N];
+        tmem_ld_cols<N>(taddr + (uint32_t)(a * BN), u);
+        tmem_ld_wait<N>(u);                                // completes the loads of v too
+#pragma unroll
+        for (int i = 0; i < N; ++i) { asm volatile("" : "+f"(v[i])); v[i] += u[i]; }
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void add_bias(float* v, const float* __restrict__ b) {     // b 8-byte aligned, N even
     if constexpr (N % 4 == 0) {
@@ -316,7 +331,9 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
     const int NT = BN * nsub;                             // columns of one output tile
     // accumulator regions of BN columns form a ring over TMEM: sub-tile number g (counted over this CTA's tiles)
     // lives in region g % nreg, so whenever nreg > nsub the next tile starts while this one is being drained
-    const int nreg = TMEM_COLS / BN < MAX_REG ? TMEM_COLS / BN : MAX_REG;
+    // Accumulator split: a region holds `accs` accumulators of BN columns, [main 0 | ... | main nmain-1 | corr]
+    const int nmain = w.nmain, accs = w.nmain + w.corr, RW = BN * accs;
+    const int nreg = TMEM_COLS / RW < MAX_REG ? TMEM_COLS / RW : MAX_REG;
 
     // 1024-byte alignment for the 128-byte swizzle atoms, as an offset so the pointers stay in the shared window
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -395,7 +412,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             for (int sub = 0; sub < nsub; ++sub) {
                 { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
                 tc_fence_after();
-                const uint32_t tbase = tmem + reg * BN + ((uint32_t)(q * 32) << 16);
+                const uint32_t tbase = tmem + reg * RW + ((uint32_t)(q * 32) << 16);
                 const int h0 = ((tile % ntn) * nsub + sub) * HPB;
                 // heads of the sub-tile alternate between the quadrant's E warps; with an odd head count the warp
                 // that takes the extra head alternates from tile to tile
@@ -407,8 +424,8 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     unsigned long long s2[8];              // scores (2a, 2a + 1) packed for fma.rn.f32x2
                     {
                         float kv[HDP], qv[HDP];
-                        tmem_ld_cols<HDP>(th + HDP, kv);
-                        tmem_ld_cols<HDP>(th, qv);
+                        tmem_ld_acc<HDP>(th + HDP, kv, accs, BN);
+                        tmem_ld_acc<HDP>(th, qv, accs, BN);
                         tmem_ld_wait<HDP>(kv);
                         tmem_ld_wait<HDP>(qv);
                         if constexpr (LNP) {
@@ -462,7 +479,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     float o[HDP];
                     {
                         float vv[HDP];
-                        tmem_ld_cols<HDP>(th + 2 * HDP, vv);
+                        tmem_ld_acc<HDP>(th + 2 * HDP, vv, accs, BN);
                         tmem_ld_wait<HDP>(vv);
                         if constexpr (LNP) ln_post<HDP>(vv, ln.cs + (bh - ep.bias) + 2 * HDP, ln.bw + (bh - ep.bias) + 2 * HDP, lmean, lrstd, lf);
                         add_bias<HDP>(vv, bh + 2 * HDP);
@@ -565,7 +582,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
             for (int sub = 0; sub < nsub; ++sub) {
                 { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
                 tc_fence_after();
-                const uint32_t tbase = tmem + reg * BN + ((uint32_t)(q * 32) << 16);
+                const uint32_t tbase = tmem + reg * RW + ((uint32_t)(q * 32) << 16);
                 for (int ch = part; ch < nch; ch += E) {
                     // bias and residual of this lane's four row segments are requested before the accumulator is
                     // read, so their latency (L2 hits: the rows were prefetched a tile ahead) overlaps the staging
@@ -579,7 +596,8 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                         for (int i = 0; i < 4; ++i) res[i] = ((okm >> i) & 1u) ? ep.resid4(cr[i], n) : zero4();
                     }
                     float v[16];
-                    tmem_ld16(tbase + (uint32_t)(ch * 16), v);
+                    tmem_ld_acc<16>(tbase + (uint32_t)(ch * 16), v, accs, BN);
+                    tmem_ld_wait<16>(v);
                     __syncwarp();                          // previous chunk's reads of the staging tile are done
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -736,6 +754,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 if (rem > KB) rem = KB;
                 const int ksteps = (rem + 7) >> 3;
                 const uint64_t a_hi = make_desc(sA + aslot * A_SLOT), a_lo = make_desc(sA + aslot * A_SLOT + BM * 128);
+                const int mj = kb % nmain;
                 uint32_t reg = reg0, rphase = rphase0;
                 for (int sub = 0; sub < nsub; ++sub) {
                     if (kb == 0) { TC_T0(t_); mbar_wait(acc_empty + 8 * reg, rphase ^ 1); TC_ACC(1, t_); }   // the epilogue drained this region
@@ -745,12 +764,15 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                     TC_T0(ti_);
                     if (elect_one()) {
                         const uint64_t b_hi = make_desc(sB + bs * b_stage), b_lo = make_desc(sB + bs * b_stage + b_img);
-                        const uint32_t d_sub = tmem + reg * BN;
+                        // accumulator split: hi*hi of this K block -> main kb % nmain; corrections -> corr (or the same main)
+                        const uint32_t d_main = tmem + reg * RW + (uint32_t)(mj * BN);
+                        const uint32_t d_corr = w.corr ? tmem + reg * RW + (uint32_t)(nmain * BN) : d_main;
+                        const bool fresh_main = kb < nmain, fresh_corr = w.corr ? kb == 0 : fresh_main;
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes >> 4 inside the swizzle row
-                            umma_tf32(d_sub, a_lo + adv, b_hi + adv, idesc, (kb | ks) ? 1u : 0u);
-                            umma_tf32(d_sub, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32(d_sub, a_hi + adv, b_hi + adv, idesc, 1u);
+                            umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, (fresh_corr && ks == 0) ? 0u : 1u);
+                            umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, (w.corr && fresh_main && ks == 0) ? 0u : 1u);
                         }
                         if (!resident) umma_commit(b_empty + 8 * bs);
                         if (kb + 1 == nkb) umma_commit(acc_full + 8 * reg);
@@ -869,29 +891,55 @@ inline cudaError_t launch_ln_stats(cudaStream_t st, const AL& al, long long M, i
 // BN columns each (BN = the UMMA N and the granularity of the weight ring; nsub * BN <= 512 TMEM columns).  The
 // A operand is produced once per output tile (~100 columns worth of tensor time per K block), so the chooser
 // takes the fewest n-tiles, then the least column padding, preferring resident weights and a >= 3 slot ring.
-struct Tiling { int BN, nsub, ntn, nkb, resident; };
+struct Tiling { int BN, nsub, ntn, nkb, resident, nmain, corr; };
 
-inline Tiling choose_tiling(int N, int K, int wide) {
+// Accumulator split of a GEMM with reduction length K.  tcgen05.mma truncates its fp32 accumulator toward zero (about
+// 0.6 ulp of the accumulator per MMA, profiles/r2_microbench_mma_acc.txt), so the error of a dot product grows with the
+// number of MMAs chained into one accumulator: with everything in one accumulator (3 K / 8 MMAs) a 3xTF32 product is
+// 3x (K = 48) to 15x (K = 1536) less accurate than an fp32 FMA chain.  The lo*hi + hi*lo corrections are ~2^-11 of the
+// result: in an accumulator of their own their truncation is invisible and the main chain shrinks to K / 8; `nmain`
+// main accumulators taking alternate K blocks cut it to K / (8 nmain) on values ~1/sqrt(nmain) as large
+// (profiles/r2_microbench_mma_split.txt).  ESCB_ACC="nmain,corr" overrides the policy at pack time (A-B and tests).
+struct AccSplit { int nmain, corr; };
+inline AccSplit acc_policy(int K, int max_accs) {
+    AccSplit a{1, 0};
+    const int nkb = (K + KB - 1) / KB;
+    if (const char* e = getenv("ESCB_ACC")) {
+        int m = 1, c = 0;
+        if (sscanf(e, "%d,%d", &m, &c) >= 1) { a.nmain = m < 1 ? 1 : (m > 4 ? 4 : m); a.corr = c ? 1 : 0; }
+    } else {
+        a.corr = K > 32 ? 1 : 0;
+        a.nmain = K >= 1024 ? 3 : (K >= 256 ? 2 : 1);      // main chains of at most ~24 MMAs (64 at K = 1536)
+    }
+    if (a.nmain > nkb) a.nmain = nkb;
+    while (a.nmain + a.corr > max_accs && a.nmain > 1) --a.nmain;
+    if (a.nmain + a.corr > max_accs) a.corr = 0;
+    return a;
+}
+
+inline Tiling choose_tiling(int N, int K, int wide, int max_accs = 4) {
     const long long B_BUDGET = b_budget(wide);
-    Tiling best{0, 0, 0, 0, 0};
+    const AccSplit as = acc_policy(K, max_accs);
+    const int accs = as.nmain + as.corr;
+    Tiling best{0, 0, 0, 0, 0, 1, 0};
     double best_cost = 1e30;
     const int nkb = (K + KB - 1) / KB;
     for (int ntn = 1; ntn <= 64; ++ntn)
         for (int nsub = 1; nsub <= MAX_REG; ++nsub) {
             const int bn = (((N + ntn * nsub - 1) / (ntn * nsub)) + 15) / 16 * 16;
-            if (bn > MAX_BN || bn * nsub > TMEM_COLS) continue;
+            if (bn > MAX_BN || bn * nsub * accs > TMEM_COLS) continue;
             if (bn < 48 && ntn * nsub > 1) continue;
             const long long stage = (long long)bn * 256;
             const bool res = stage * nkb * nsub <= B_BUDGET && nkb * nsub <= MAX_NB;
             const int nb = res ? nkb * nsub : (int)(B_BUDGET / stage);
             if (!res && nb < 2) continue;
             const double padn = (double)bn * nsub * ntn;
-            const int nreg = TMEM_COLS / bn < MAX_REG ? TMEM_COLS / bn : MAX_REG;
+            const int nreg = TMEM_COLS / (bn * accs) < MAX_REG ? TMEM_COLS / (bn * accs) : MAX_REG;
             // an SS-mode MMA reads (128 + bn) * 32 bytes of shared memory per bn / 2 clocks: wider is cheaper per MAC
             const double narrow = ntn * nsub > 1 ? (bn < 96 ? 0.3 : (bn < 128 ? 0.15 : (bn < 176 ? 0.05 : 0.0))) : 0.0;
             const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + (nreg <= nsub ? 0.15 : 0.0) + narrow) +
                                 96.0 * ntn + 4.0 * nsub;
-            if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0}; }
+            if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0, as.nmain, as.corr}; }
         }
     return best;
 }
@@ -900,7 +948,8 @@ inline Tiling choose_tiling(int N, int K, int wide) {
 // kAttnBN = 144 columns (HPB whole heads); as many sub-tiles per output tile as TMEM holds (3), evenly split.
 inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const int nkb = (K + KB - 1) / KB;
-    const int max_sub = TMEM_COLS / 144;
+    const AccSplit as = acc_policy(K, TMEM_COLS / 144);
+    const int max_sub = TMEM_COLS / (144 * (as.nmain + as.corr));
     // fewest padded (all-zero) sub-tiles first, then the most sub-tiles per output tile (A is produced once per tile)
     int ntn = 1, nsub = 1, best_waste = 1 << 30;
     for (int ns = max_sub; ns >= 1; --ns) {
@@ -910,7 +959,7 @@ inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const long long stage = 144LL * 256;
     const bool res = stage * nkb * nsub <= b_budget_attn() && nkb * nsub <= MAX_NB;
     if (ntn_out_subs) *ntn_out_subs = ntn * nsub;
-    return Tiling{144, nsub, ntn, nkb, res ? 1 : 0};
+    return Tiling{144, nsub, ntn, nkb, res ? 1 : 0, as.nmain, as.corr};
 }
 
 // Per-device caches: a process may drive several GPUs (codec.py keeps one handle per device), and both the SM count
