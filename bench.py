@@ -336,7 +336,49 @@ def small_batch_latency(model, dev, batch=1, iters=50):
     return out
 
 
-def incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, steps):
+def flip_census(cfg, dev, ref_model, my_model, batches=4, per=36):
+    """Code decisions that differ from the reference's (CPU, fp32) over `batches` x `per` fresh clips, for three
+    implementations of the same fp32 arithmetic: the reference itself run on this GPU, this library's tcgen05 engine
+    (the product path) and this library's fp32 SIMT engine.  A clip counts once: after its first differing decision the
+    residual chain diverges, so later codes of the same clip are not independent events."""
+    import torch
+    from escb200.codec import ESC
+    from escb200.spec import CodecSpec
+    from escb200.synthetic import synth_audio, synth_state_dict
+    old_env = os.environ.get("ESCB_GEMM")
+    os.environ["ESCB_GEMM"] = "simt"                      # read when the native handle is created
+    try:
+        simt = ESC(**cfg)
+        simt.load_state_dict(synth_state_dict(CodecSpec.from_kwargs(**cfg), 0))
+        simt = simt.eval().to(dev)
+        simt.encode(synth_audio(1, CLIP_SAMPLES, seed=1).to(dev), 6)
+    finally:
+        if old_env is None:
+            del os.environ["ESCB_GEMM"]
+        else:
+            os.environ["ESCB_GEMM"] = old_env
+    cpu_model = ref_model.to("cpu")
+    ref_cpu = []
+    xs = [synth_audio(per, CLIP_SAMPLES, seed=1000 + b) for b in range(batches)]     # batch 0 = the bench input of rank 0
+    with torch.no_grad():
+        for x in xs:
+            ref_cpu.append(cpu_model.encode(x, 6)[0])
+        gpu_model = ref_model.to(dev)
+        out = {"clips": batches * per, "codes_per_clip": int(ref_cpu[0][0].numel()),
+               "what": "clips with at least one code index different from the reference on the CPU (fp32 ATen)"}
+        for name, enc in (("reference_on_this_gpu", lambda x: gpu_model.encode(x, 6)[0]),
+                          ("escb200_tcgen05", lambda x: my_model.encode(x, 6)[0]),
+                          ("escb200_fp32_simt", lambda x: simt.encode(x, 6)[0])):
+            clips, codes = 0, 0
+            for x, rc in zip(xs, ref_cpu):
+                bad = enc(x.to(dev)).cpu() != rc
+                clips += int((bad.flatten(1).sum(1) > 0).sum())
+                codes += int(bad.sum())
+            out[name] = {"clips_with_a_flip": clips, "codes_differing": codes}
+    return out
+
+
+def incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, steps, my_model=None):
     """The reference itself in eager PyTorch ON THIS GPU (fp32, TF32 off for matmul and cuDNN): the practical incumbent,
     since the reference has no native kernels - plus the parity noise floor reference-CPU vs reference-GPU."""
     import torch
@@ -374,7 +416,13 @@ def incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, steps):
             e1.record()
             torch.cuda.synchronize(dev)
             ms = e0.elapsed_time(e1) / n
-        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B,
+        census = None
+        if my_model is not None:
+            try:
+                census = flip_census(cfg, dev, model, my_model)
+            except Exception as e:
+                census = {"error": repr(e)[:200]}
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B, "flip_census": census,
                 "what": "reference esc.ESC.encode+decode, eager PyTorch on this B200, fp32, allow_tf32=False (matmul and cuDNN)",
                 "noise_floor": {
                     "clips": n_cpu, "codes_per_clip": int(c_cpu[0].numel()),
@@ -626,7 +674,8 @@ def main_b200(args):
             extra["latency_b1"] = small_batch_latency(model, dev, 1)
         # ---- the reference in eager PyTorch on this GPU + parity noise floor
         my_codes, my_audio = step_device(x_dev, S, gather=False)
-        extra["incumbent"] = incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, args.steps)
+        extra["incumbent"] = incumbent_and_noise_floor(cfg, dev, x_dev, my_codes, my_audio, args.steps,
+                                                       my_model=model if (args.config == "base" and N == 1) else None)
         # ---- BASELINE configs[2]: ESC-Large, batch 64
         if args.config == "base" and N == 1:
             del my_codes, my_audio

@@ -72,6 +72,7 @@ struct escb_handle {
     int ln_post = kLnPostDefault;   // ESCB_LN_POST bit mask (internal.h)
     bool fuse_pvq = true;      // ESCB_FUSE_PVQ=0: three launches per RVQ stream step (down GEMM, argmin, up GEMM)
     bool emit_stats = true;    // ESCB_EMIT_STATS=0: every LayerNorm GEMM runs its own statistics pre-kernel (A/B debugging)
+    int fuse_mlp_max_c = 1 << 30;   // ESCB_FUSE_MLP_MAXC: widest level that takes the fused MLP kernel (where a plan exists)
     bool fuse_mlp = true;      // ESCB_FUSE_MLP=0 keeps the unfused mlp1 + mlp2 pair everywhere (A/B debugging, variant tests)
     int fuse_attn_max_c = 1 << 20;   // ESCB_FUSE_ATTN_MAXC: widest layer whose qkv GEMM runs the attention core in its epilogue (0: never)
     Profiler* prof = nullptr;  // escb_profile_begin .. escb_profile_end (debug facility, single caller)
@@ -808,7 +809,7 @@ static void run_layer(Ctx& c, int li, const float* x_in, float* xw, float* out, 
         }
         op_proj(c.L, bw, c.wk.att, ld, src, xw, ld, g, Mw);
         have_stats = false;
-        if (c.L.fuse_mlp && bw.mlpf.plan.ok) {
+        if (c.L.fuse_mlp && bw.mlpf.plan.ok && C <= c.h->fuse_mlp_max_c) {
             // the rows this kernel writes are the input of the next LayerNorm: let its epilogue emit their statistics
             mf::StatsOut so{};
             if (c.L.emit_stats) {
@@ -1053,6 +1054,7 @@ int escb_create(const escb_config* cfg, escb_handle** out) {
     if (const char* e = getenv("ESCB_PVQ")) h->pvq_tc = strcmp(e, "simt") != 0;
     if (const char* e = getenv("ESCB_FUSE_ATTN_MAXC")) h->fuse_attn_max_c = atoi(e);
     if (const char* e = getenv("ESCB_FUSE_MLP")) h->fuse_mlp = atoi(e) != 0;
+    if (const char* e = getenv("ESCB_FUSE_MLP_MAXC")) h->fuse_mlp_max_c = atoi(e);
     if (const char* e = getenv("ESCB_EMIT_STATS")) h->emit_stats = atoi(e) != 0;
     if (const char* e = getenv("ESCB_FUSE_PVQ")) h->fuse_pvq = atoi(e) != 0;
     if (const char* e = getenv("ESCB_LN_POST")) h->ln_post = atoi(e);

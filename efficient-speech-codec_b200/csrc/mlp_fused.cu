@@ -19,6 +19,7 @@ struct Params {
     int nboxf, rem;                 // x tile = nboxf full 32-column boxes + a remainder of `rem` columns (dense rows)
     unsigned st2_bytes, slot_bytes, chunk_bytes, xslot_bytes;
     int col_a1, col_r, col_l, col_acc;
+    int corr2;                      // 1: fc2 corrections accumulate at col_acc + (nacc + ab) * N2
     const float* w_img;             // per chunk: fc1 stages kb = 0..nkb1-1, then fc2 stages kb = 0, 1
     const float* b1;                // [nch * 64], zero padded
     const float* b2;                // [N2]
@@ -311,16 +312,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
         const uint32_t idesc2 = make_idesc(N2);
         uint32_t wslot = 0, wphase = 0;
         // one K block of fc2: A = the GELU chunk (hi in R, lo in L), accumulating into ACC2
-        auto issue2 = [&](uint32_t saddr, int kb, uint32_t a_hi, uint32_t a_lo, uint32_t d, bool first) {
+        auto issue2 = [&](uint32_t saddr, int kb, uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t dc, bool first) {
             const uint64_t b_hi = make_desc(saddr), b_lo = make_desc(saddr + (uint32_t)N2 * 128);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t ac = (uint32_t)((4 * kb + ks) * 8);
                 const uint64_t adv = (uint64_t)(ks * 2);
-                umma_ts_tf32(d, a_lo + ac, b_hi + adv, idesc2, (first && kb == 0 && ks == 0) ? 0u : 1u);
+                const uint32_t fresh = (first && kb == 0 && ks == 0) ? 0u : 1u;
+                umma_ts_tf32(dc, a_lo + ac, b_hi + adv, idesc2, fresh);
                 if (p.dbg & 4) continue;
-                umma_ts_tf32(d, a_hi + ac, b_lo + adv, idesc2, 1u);
-                umma_ts_tf32(d, a_hi + ac, b_hi + adv, idesc2, 1u);
+                umma_ts_tf32(dc, a_hi + ac, b_lo + adv, idesc2, 1u);
+                umma_ts_tf32(d, a_hi + ac, b_hi + adv, idesc2, p.corr2 ? fresh : 1u);
             }
         };
         for (int c = 0; c < total; ++c) {
@@ -330,6 +332,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
             const uint32_t a_hi = tmem + (uint32_t)(p.col_r + (c & 1) * HC);
             const uint32_t a_lo = tmem + (uint32_t)(p.col_l + (p.nl == 2 ? (c & 1) : 0) * HC);
             const uint32_t d = tmem + (uint32_t)(p.col_acc + ab * N2);
+            const uint32_t dc = p.corr2 ? tmem + (uint32_t)(p.col_acc + (p.nacc + ab) * N2) : d;
             MF_TL(3, c);
             if (p.resident) {
                 if (c < NCH)
@@ -337,8 +340,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t base = sW2 + (uint32_t)j * 2u * ST2;
-                    issue2(base, 0, a_hi, a_lo, d, j == 0);
-                    issue2(base + ST2, 1, a_hi, a_lo, d, j == 0);
+                    issue2(base, 0, a_hi, a_lo, d, dc, j == 0);
+                    issue2(base + ST2, 1, a_hi, a_lo, d, dc, j == 0);
                     umma_commit(bar(B_RFREE + (c & 1)));
                     if (p.nl == 1) umma_commit(bar(B_LFREE));
                     if (j + 1 == NCH) umma_commit(bar(B_ACCFULL + ab));
@@ -350,7 +353,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
                     MF_WAIT(3, bar(B_W2FULL + wslot), wphase);
                     tc_fence_after();
                     if (elect_one()) {
-                        issue2(sW2 + wslot * ST2, kb, a_hi, a_lo, d, j == 0);
+                        issue2(sW2 + wslot * ST2, kb, a_hi, a_lo, d, dc, j == 0);
                         umma_commit(bar(B_W2FREE + wslot));
                         if (kb == 1) {
                             umma_commit(bar(B_RFREE + (c & 1)));
@@ -510,9 +513,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
                     }
                 }
             };
+            const int accs2 = 1 + p.corr2, cstride = p.nacc * N2;      // main + corrections, cstride columns apart
             {
                 float v0[R0];
-                tmem_ld_cols<R0>(t_acc, v0);
+                tmem_ld_acc<R0>(t_acc, v0, accs2, cstride);
                 tmem_ld_wait<R0>(v0);
                 if (R1 == 0) {
                     tc_fence_before();
@@ -523,7 +527,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap mapLf, const __grid_constan
             }
             if (R1 > 0) {
                 float v1[R1 > 0 ? R1 : 16];
-                tmem_ld_cols<(R1 > 0 ? R1 : 16)>(t_acc + (uint32_t)R0, v1);
+                tmem_ld_acc<(R1 > 0 ? R1 : 16)>(t_acc + (uint32_t)R0, v1, accs2, cstride);
                 tmem_ld_wait<(R1 > 0 ? R1 : 16)>(v1);
                 tc_fence_before();
                 __syncwarp();
@@ -661,7 +665,7 @@ cudaError_t launch(cudaStream_t st, const Weights& w, float* x, long long M, flo
     p.nx = pl.nx; p.na1 = pl.na1; p.nl = pl.nl; p.nacc = pl.nacc; p.resident = pl.resident; p.ns1 = pl.ns1; p.ns2 = pl.ns2;
     p.nboxf = pl.nboxf; p.rem = pl.rem;
     p.st2_bytes = pl.st2_bytes; p.slot_bytes = pl.slot_bytes; p.chunk_bytes = pl.chunk_bytes; p.xslot_bytes = pl.xslot_bytes;
-    p.col_a1 = pl.col_a1; p.col_r = pl.col_r; p.col_l = pl.col_l; p.col_acc = pl.col_acc;
+    p.col_a1 = pl.col_a1; p.col_r = pl.col_r; p.col_l = pl.col_l; p.col_acc = pl.col_acc; p.corr2 = pl.corr2;
     p.w_img = w.img; p.b1 = w.b1; p.b2 = w.b2; p.gamma = w.gamma; p.beta = w.beta;
     p.eps = eps;
     p.M = M;

@@ -23,7 +23,7 @@
 // partial product of that chunk accumulated into ACC2.  The MMA warp issues ... G2(c-2), G1(c), G2(c-1), G1(c+1) ... so
 // the tensor pipe works on G1 of the next chunks while the GELU warps convert the current one.
 //
-// TMEM columns (512): A1 images 2 * Kp16 per buffer | R0, R1 (64 each) | L0[, L1] (64 each) | ACC2 (N2 per buffer).
+// TMEM columns (512): A1 images 2 * Kp16 per buffer | R0, R1 (64 each) | L0[, L1] (64 each) | ACC2 (N2 per buffer) [| ACC2 corrections].
 // Precision: identical to the unfused tcgen05 path (same 3xTF32 split, same k order, same bias / GELU / residual
 // arithmetic); only the LayerNorm sums are accumulated per thread instead of by 8 lanes.
 #pragma once
@@ -76,6 +76,7 @@ struct Plan {                       // geometry of the fused kernel for one chan
     int C, ld, Kp16, ksteps1, nkb1, nch, N2, nx, na1, nl, nacc, resident, ns1, ns2, nboxf, rem;
     unsigned st2_bytes, slot_bytes, chunk_bytes, xslot_bytes;
     int col_a1, col_r, col_l, col_acc;
+    int corr2;                      // fc2's lo*hi + hi*lo corrections accumulate in a region of their own behind ACC2 (tc_gemm.cuh acc_policy)
     size_t smem_bytes;
     size_t img_floats;              // weight blob size
 };
@@ -100,7 +101,12 @@ inline Plan make_plan(int C, int hidden) {
     // TMEM: A1 buffers | R0 R1 | L buffers | ACC2 buffers
     const int fixed = 2 * HC;
     pl.na1 = 1; pl.nl = 1; pl.nacc = 1;
-    auto cols = [&](int na1, int nl, int nacc) { return na1 * 2 * pl.Kp16 + fixed + nl * HC + nacc * pl.N2; };
+    // fc2 reduces over 4C = 180..384 hidden units (68..144 MMAs in one accumulator): its corrections get their own
+    // accumulator where TMEM has the columns (C = 45, 72; ESCB_MF_CORR=0 keeps one accumulator, A-B builds)
+    pl.corr2 = 1;
+    if (const char* e = getenv("ESCB_MF_CORR")) pl.corr2 = atoi(e) ? 1 : 0;
+    if (2 * pl.Kp16 + fixed + HC + 2 * pl.N2 > 512) pl.corr2 = 0;
+    auto cols = [&](int na1, int nl, int nacc) { return na1 * 2 * pl.Kp16 + fixed + nl * HC + nacc * pl.N2 * (1 + pl.corr2); };
     if (cols(1, 1, 1) > 512) return pl;
     if (cols(1, 2, 1) <= 512) pl.nl = 2;
     if (cols(2, pl.nl, 1) <= 512) pl.na1 = 2;

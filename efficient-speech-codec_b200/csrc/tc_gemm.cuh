@@ -896,24 +896,35 @@ struct Tiling { int BN, nsub, ntn, nkb, resident, nmain, corr; };
 // Accumulator split of a GEMM with reduction length K.  tcgen05.mma truncates its fp32 accumulator toward zero (about
 // 0.6 ulp of the accumulator per MMA, profiles/r2_microbench_mma_acc.txt), so the error of a dot product grows with the
 // number of MMAs chained into one accumulator: with everything in one accumulator (3 K / 8 MMAs) a 3xTF32 product is
-// 3x (K = 48) to 15x (K = 1536) less accurate than an fp32 FMA chain.  The lo*hi + hi*lo corrections are ~2^-11 of the
-// result: in an accumulator of their own their truncation is invisible and the main chain shrinks to K / 8; `nmain`
-// main accumulators taking alternate K blocks cut it to K / (8 nmain) on values ~1/sqrt(nmain) as large
-// (profiles/r2_microbench_mma_split.txt).  ESCB_ACC="nmain,corr" overrides the policy at pack time (A-B and tests).
-struct AccSplit { int nmain, corr; };
+// 3x (K = 48) to 15x (K = 1536) less accurate than an fp32 FMA chain, and 12 of 288 bench clips had a code decision
+// that differs from the reference's (the fp32 SIMT engine: 3, all split policies: 3-4; profiles/r2_acc_sweep*.txt).
+// The lo*hi + hi*lo corrections are ~2^-11 of the result: in an accumulator of their own their truncation is invisible
+// and the main chain shrinks to K / 8; `nmain` main accumulators taking alternate K blocks cut it to K / (8 nmain) on
+// values ~1/sqrt(nmain) as large (profiles/r2_microbench_mma_split.txt).  Policy (`nmain` = what must fit, `want` = what
+// is taken when it costs neither an extra n-tile nor the last double-buffered region): reductions up to 96 keep one
+// accumulator (chains <= 36 MMAs, the three top levels, where TMEM pays for tile overlap), longer ones split off the
+// corrections, K >= 1024 also gets a second main.  ESCB_ACC="nmain,corr" / ESCB_ACC_KMIN override it at pack time.
+struct AccSplit { int nmain, corr, want; };
 inline AccSplit acc_policy(int K, int max_accs) {
-    AccSplit a{1, 0};
+    AccSplit a{1, 0, 1};
     const int nkb = (K + KB - 1) / KB;
+    int kmin = 97;
+    if (const char* e = getenv("ESCB_ACC_KMIN")) kmin = atoi(e);
     if (const char* e = getenv("ESCB_ACC")) {
         int m = 1, c = 0;
-        if (sscanf(e, "%d,%d", &m, &c) >= 1) { a.nmain = m < 1 ? 1 : (m > 4 ? 4 : m); a.corr = c ? 1 : 0; }
+        if (sscanf(e, "%d,%d", &m, &c) >= 1) { a.nmain = m < 1 ? 1 : (m > 4 ? 4 : m); a.corr = c ? 1 : 0; a.want = a.nmain; }
     } else {
-        a.corr = K > 32 ? 1 : 0;
-        a.nmain = K >= 1024 ? 3 : (K >= 256 ? 2 : 1);      // main chains of at most ~24 MMAs (64 at K = 1536)
+        a.corr = 1;
+        a.nmain = K >= 1024 ? 2 : 1;
+        a.want = K >= 1024 ? 3 : (K >= 256 ? 2 : 1);
     }
+    if (K < kmin) a = AccSplit{1, 0, 1};
     if (a.nmain > nkb) a.nmain = nkb;
     while (a.nmain + a.corr > max_accs && a.nmain > 1) --a.nmain;
     if (a.nmain + a.corr > max_accs) a.corr = 0;
+    if (a.want > nkb) a.want = nkb;
+    if (a.want + a.corr > max_accs) a.want = max_accs - a.corr;
+    if (a.want < a.nmain) a.want = a.nmain;
     return a;
 }
 
@@ -941,6 +952,12 @@ inline Tiling choose_tiling(int N, int K, int wide, int max_accs = 4) {
                                 96.0 * ntn + 4.0 * nsub;
             if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0, as.nmain, as.corr}; }
         }
+    // free upgrades: more main accumulators while the tile still fits TMEM and keeps its region ring (or had none)
+    while (best.BN > 0 && best.nmain < as.want && best.BN * best.nsub * (best.nmain + 1 + best.corr) <= TMEM_COLS) {
+        const int nreg0 = TMEM_COLS / (best.BN * (best.nmain + best.corr)), nreg1 = TMEM_COLS / (best.BN * (best.nmain + 1 + best.corr));
+        if (nreg1 < nreg0 && (nreg1 < 2 || nreg1 <= best.nsub)) break;
+        ++best.nmain;
+    }
     return best;
 }
 
@@ -959,7 +976,13 @@ inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const long long stage = 144LL * 256;
     const bool res = stage * nkb * nsub <= b_budget_attn() && nkb * nsub <= MAX_NB;
     if (ntn_out_subs) *ntn_out_subs = ntn * nsub;
-    return Tiling{144, nsub, ntn, nkb, res ? 1 : 0, as.nmain, as.corr};
+    int nmain = as.nmain;                                  // free upgrade, as in choose_tiling
+    while (nmain < as.want && 144 * nsub * (nmain + 1 + as.corr) <= TMEM_COLS) {
+        const int nreg0 = TMEM_COLS / (144 * (nmain + as.corr)), nreg1 = TMEM_COLS / (144 * (nmain + 1 + as.corr));
+        if (nreg1 < nreg0 && (nreg1 < 2 || nreg1 <= nsub)) break;
+        ++nmain;
+    }
+    return Tiling{144, nsub, ntn, nkb, res ? 1 : 0, nmain, as.corr};
 }
 
 // Per-device caches: a process may drive several GPUs (codec.py keeps one handle per device), and both the SM count

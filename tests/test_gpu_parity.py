@@ -282,11 +282,14 @@ def test_full_batch_properties(base0):
 
 @pytest.mark.parametrize("env", [{"ESCB_FUSE_ATTN_MAXC": "0"}, {"ESCB_FUSE_ATTN_MAXC": "96"}, {"ESCB_GEMM": "simt"},
                                  {"ESCB_LN_POST": "7"}, {"ESCB_LN_POST": "0"}, {"ESCB_FUSE_MLP": "0"}, {"ESCB_FUSE_PVQ": "0"}, {"ESCB_EMIT_STATS": "0"},
-                                 {"ESCB_FUSE_MLP": "0", "ESCB_FUSE_ATTN_MAXC": "0"}])
+                                 {"ESCB_FUSE_MLP": "0", "ESCB_FUSE_ATTN_MAXC": "0"},
+                                 {"ESCB_ACC": "1,0", "ESCB_MF_CORR": "0"}, {"ESCB_ACC": "2,1"}, {"ESCB_ACC": "4,1", "ESCB_FUSE_MLP": "0"},
+                                 {"ESCB_ACC": "3,0", "ESCB_ACC_KMIN": "0"}])
 def test_engine_variants_agree(base0, env, monkeypatch):
     """The fused qkv+attention kernel, the unfused qkv GEMM + window_attn_kernel pair, the fp32 SIMT engine, the fused
     MLP kernel (LN2 -> fc1 -> GELU -> fc2 -> +x in one launch, the default for C <= 96) against the mlp1 + mlp2 pair, and the
-    LayerNorm placement (in the A producers / after the GEMM on a gamma-folded weight) are alternative
+    LayerNorm placement (in the A producers / after the GEMM on a gamma-folded weight) and the accumulator split of the
+    tcgen05 engine (ESCB_ACC = "mains,corrections": one accumulator, the default policy, forced wider splits) are alternative
     implementations of the same layers: identical code indices, audio equal to fp32 reassociation noise
     (ragged width: padded windows + shift masks on every level)."""
     x = synth_audio(3, 16000 + 80 * 4 * 7, seed=41).cuda()
@@ -300,6 +303,36 @@ def test_engine_variants_agree(base0, env, monkeypatch):
     assert fs0 == fs1
     assert torch.equal(codes0, codes1)
     assert maxabs(audio0.cpu(), audio1.cpu()) <= 2e-5
+
+
+def test_bench_batch_bit_exact_against_oracle(base0):
+    """BASELINE configs[1] at full size: every code index of the bench's 36 clips equals the oracle's, audio within
+    tolerance.  With all MMAs of a dot product chained into ONE TMEM accumulator (ESCB_ACC=1,0) three of these clips
+    (12, 15, 22) flip a near-tie decision: tcgen05.mma truncates its accumulator (tc_gemm.cuh acc_policy)."""
+    x = synth_audio(36, 48000, seed=1000)
+    codes, fs = base0.encode(x.cuda(), 6)
+    audio = base0.decode(codes, fs)
+    o = make_oracle(BASE, 0)[0]
+    co, _ = o.encode(x, 6)
+    bad = (co != codes.cpu()).flatten(1).sum(1)
+    assert int((bad > 0).sum()) == 0, f"clips with a differing code: {torch.nonzero(bad).flatten().tolist()}"
+    assert maxabs(o.decode(co, fs), audio.cpu()) <= AUDIO_TOL
+
+
+def test_deep_layer_error_is_fp32_grade(base0):
+    """The C = 384 layer (K up to 1536) against a float64 evaluation of the oracle: with the accumulator split the
+    tcgen05 engine is within 2.5x of what fp32 arithmetic gives (1.0e-6 on the SIMT engine; 9.8e-6 with one accumulator)."""
+    from oracle.esc_oracle import OracleConfig, swin_layer
+    from escb200.spec import CodecSpec
+    from escb200.synthetic import synth_state_dict
+    sd = synth_state_dict(CodecSpec.from_kwargs(**BASE), 0)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    c = OracleConfig(**BASE)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 2 * 300, c.dec_h_dims[0], generator=g)
+    ref, _, _ = swin_layer(sd64, "decoder.blocks.0", x.double(), 2, 300, c.dec_heads[0], c.swin_depth, c.window_size, "up")
+    y = Unit(base0).swin_layer(6, x, 2, 300, tuple(ref.shape)).double()
+    assert float((y - ref).abs().max() / ref.abs().max()) <= 2.5e-6
 
 
 @pytest.mark.parametrize("alt", ["", "0", "1"])
