@@ -135,9 +135,12 @@ constexpr int kSplitWide = ESCB_ROLE_SPLIT;      // PatchSplit GEMM role split
 #endif
 constexpr int kProjWide = ESCB_ROLE_PROJ;       // attention output projection role split
 #ifndef ESCB_ROLE_MLP2
-#define ESCB_ROLE_MLP2 0
+#define ESCB_ROLE_MLP2 1
 #endif
-constexpr int kMlp2Wide = ESCB_ROLE_MLP2;       // mlp2 (K = 4N): 8 + 16 measured 4.65 ms, 16 + 8 5.01 ms
+// mlp2 (K = 4N).  Round 1 (every level, one accumulator): 8 + 16 measured 4.65 ms, 16 + 8 5.01 ms.  Since the fused MLP
+// kernel took C <= 96 and the accumulator split left the deeper levels ONE accumulator region (MMAs and epilogue of a
+// tile alternate), the epilogue is on the critical path: 16 + 8 measured 2.50 ms, 12 + 12 2.79, 8 + 16 3.06.
+constexpr int kMlp2Wide = ESCB_ROLE_MLP2;
 #ifndef ESCB_ROLE_MLP1
 #define ESCB_ROLE_MLP1 2
 #endif

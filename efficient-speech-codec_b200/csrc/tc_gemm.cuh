@@ -905,11 +905,14 @@ struct Tiling { int BN, nsub, ntn, nkb, resident, nmain, corr; };
 // accumulator (chains <= 36 MMAs, the three top levels, where TMEM pays for tile overlap), longer ones split off the
 // corrections, K >= 1024 also gets a second main.  ESCB_ACC="nmain,corr" / ESCB_ACC_KMIN override it at pack time.
 struct AccSplit { int nmain, corr, want; };
-inline AccSplit acc_policy(int K, int max_accs) {
+inline AccSplit acc_policy(int K, int max_accs, bool attn = false) {
     AccSplit a{1, 0, 1};
     const int nkb = (K + KB - 1) / KB;
-    int kmin = 97;
-    if (const char* e = getenv("ESCB_ACC_KMIN")) kmin = atoi(e);
+    // The fused attention kernel's sub-tiles are 144 columns: a second accumulator leaves one region and one sub-tile
+    // per output tile (A produced 2-4x as often, MMAs serialised with the attention epilogue: +22 % at C = 144, +42 % at
+    // C = 192), so it keeps one accumulator up to K = 192 (chains <= 72 MMAs, ~1.3e-6 rms) and splits at C = 384.
+    int kmin = attn ? 193 : 97;
+    if (const char* e = getenv(attn ? "ESCB_ACC_KMIN_ATTN" : "ESCB_ACC_KMIN")) kmin = atoi(e);
     if (const char* e = getenv("ESCB_ACC")) {
         int m = 1, c = 0;
         if (sscanf(e, "%d,%d", &m, &c) >= 1) { a.nmain = m < 1 ? 1 : (m > 4 ? 4 : m); a.corr = c ? 1 : 0; a.want = a.nmain; }
@@ -948,7 +951,11 @@ inline Tiling choose_tiling(int N, int K, int wide, int max_accs = 4) {
             const int nreg = TMEM_COLS / (bn * accs) < MAX_REG ? TMEM_COLS / (bn * accs) : MAX_REG;
             // an SS-mode MMA reads (128 + bn) * 32 bytes of shared memory per bn / 2 clocks: wider is cheaper per MAC
             const double narrow = ntn * nsub > 1 ? (bn < 96 ? 0.3 : (bn < 128 ? 0.15 : (bn < 176 ? 0.05 : 0.0))) : 0.0;
-            const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + (nreg <= nsub ? 0.15 : 0.0) + narrow) +
+            // accumulator regions: with nreg == nsub the MMAs of the next tile wait for the epilogue of this one (all of
+            // it when the tile is ONE sub-tile, the first 1 / nsub of it otherwise); full overlap needs nreg >= 2 nsub
+            static const double serial_w = getenv("ESCB_TILE_SERIAL") ? atof(getenv("ESCB_TILE_SERIAL")) : 0.15;
+            const double serial = nreg >= 2 * nsub ? 0.0 : (nreg > nsub ? 0.5 * serial_w : (accs > 1 ? 2.0 * serial_w / nsub : serial_w));
+            const double cost = padn * (1.0 + (res ? 0.0 : 0.15) + serial + narrow) +
                                 96.0 * ntn + 4.0 * nsub;
             if (cost < best_cost) { best_cost = cost; best = Tiling{bn, nsub, ntn, nkb, res ? 1 : 0, as.nmain, as.corr}; }
         }
@@ -965,7 +972,7 @@ inline Tiling choose_tiling(int N, int K, int wide, int max_accs = 4) {
 // kAttnBN = 144 columns (HPB whole heads); as many sub-tiles per output tile as TMEM holds (3), evenly split.
 inline Tiling attn_tiling(int nsubs_total, int K, int* ntn_out_subs = nullptr) {
     const int nkb = (K + KB - 1) / KB;
-    const AccSplit as = acc_policy(K, TMEM_COLS / 144);
+    const AccSplit as = acc_policy(K, TMEM_COLS / 144, true);
     const int max_sub = TMEM_COLS / (144 * (as.nmain + as.corr));
     // fewest padded (all-zero) sub-tiles first, then the most sub-tiles per output tile (A is produced once per tile)
     int ntn = 1, nsub = 1, best_waste = 1 << 30;

@@ -10,6 +10,9 @@ if os.environ.get("_PL_CHILD"):
     sys.path.insert(0, os.path.join(ROOT, "efficient-speech-codec_b200"))
     sys.path.insert(0, ROOT)
     import torch
+    if os.environ.get("PL_LIB"):                       # another build of the library (csrc/Makefile `variant`)
+        from escb200 import native
+        native.library_path = lambda: os.path.abspath(os.environ["PL_LIB"])
     from bench import BASE
     from escb200.codec import ESC
     from escb200.spec import CodecSpec
