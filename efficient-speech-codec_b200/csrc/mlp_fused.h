@@ -111,6 +111,12 @@ inline Plan make_plan(int C, int hidden) {
     if (cols(1, 2, 1) <= 512) pl.nl = 2;
     if (cols(2, pl.nl, 1) <= 512) pl.na1 = 2;
     else if (cols(1, pl.nl, 2) <= 512) pl.nacc = 2;
+    if (const char* e = getenv("ESCB_MF_BUF")) {           // experiments: "na1,nl,nacc" buffer counts (taken when they fit)
+        int a = 1, l = 1, c = 1;
+        if (sscanf(e, "%d,%d,%d", &a, &l, &c) == 3 && a >= 1 && a <= 2 && l >= 1 && l <= 2 && c >= 1 && c <= 2 && cols(a, l, c) <= 512) {
+            pl.na1 = a; pl.nl = l; pl.nacc = c;
+        }
+    }
     pl.col_a1 = 0;
     pl.col_r = pl.na1 * 2 * pl.Kp16;
     pl.col_l = pl.col_r + fixed;
