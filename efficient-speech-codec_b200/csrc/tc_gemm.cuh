@@ -60,10 +60,18 @@ constexpr int NBARS = 2 * MAX_NA + 2 * MAX_NB + 2 * MAX_REG;
 // default, producer-heavy layers such as mlp2); E = 4: 16 + 8, 2 A slots (epilogue-heavy layers: proj, PatchSplit,
 // the PVQ up-projection); E = 3: 12 + 12, where a producer thread owns rows r0, r0 + 48 and - for r0 < 32 only -
 // r0 + 96 (the GELU GEMM and the fused attention kernel, which are lopsided either way with 8 + 16 or 16 + 8).
-template <int E, bool ATTN = false>
+// PW: producer warps (0: 24 - epilogue warps).  The fused attention kernel of the top level (head width 15, C = 45)
+// runs 12 + 8: its A operand is two K blocks per tile, eight producer warps keep up, and the smaller CTA (704 threads)
+// lifts the register cap from 72 to 88, which the attention core - the critical role, a long dependent chain per
+// thread - uses (275.7 -> 253.4 us per launch; the deeper levels, which need the producers, measured 3-7 % slower).
+#ifndef ESCB_ATTN_PROD15
+#define ESCB_ATTN_PROD15 8
+#endif
+template <int E, bool ATTN = false, int PW = 0>
 struct Roles {
     static constexpr int EPI_WARPS = 4 * E;
-    static constexpr int PROD_WARPS = 24 - EPI_WARPS;
+    static constexpr int PROD_WARPS = PW > 0 ? PW : 24 - EPI_WARPS;
+    static constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 2) * 32;
     static constexpr int PROD_THREADS = PROD_WARPS * 32;
     static constexpr int RPT = (32 + PROD_WARPS - 1) / PROD_WARPS;   // rows per producer thread: 2, 3 (12 warps: the last one only for r0 < 32) or 4
     static constexpr int ROW_STEP = 4 * PROD_WARPS;        // distance between a thread's rows
@@ -276,6 +284,11 @@ __device__ __forceinline__ void ln_post(float* v, const float* __restrict__ cs, 
 template <class T, class = void> struct IsAttn { static constexpr bool value = false; };
 template <class T> struct IsAttn<T, decltype((void)T::kAttn)> { static constexpr bool value = true; };
 
+// producer-warp override per epilogue type (see Roles)
+template <class T, class = void> struct AttnProd { static constexpr int value = 0; };
+template <class T> struct AttnProd<T, decltype((void)T::kAttn)> { static constexpr int value = T::HD == 15 ? ESCB_ATTN_PROD15 : 0; };
+template <int E, class EP> using RolesFor = Roles<E, IsAttn<EP>::value, AttnProd<EP>::value>;
+
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart; version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -313,11 +326,11 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 #endif
 
 template <bool LN, class AL, class EP, int E, bool LNP = false>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__((RolesFor<E, EP>::THREADS), 1)
 tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long M, const EP ep, const int ntiles,
                const int NB, const int resident, const int pf_dist) {
     static_assert(sizeof(typename EP::Row) <= 16, "epilogue row context must fit 16 bytes");
-    using R = Roles<E, IsAttn<EP>::value>;
+    using R = RolesFor<E, EP>;
     constexpr int EPI_WARPS = R::EPI_WARPS, PROD_WARPS = R::PROD_WARPS, PROD_THREADS = R::PROD_THREADS;
     constexpr int RPT = R::RPT, ROW_STEP = R::ROW_STEP, DEPTH = R::DEPTH, NA = R::NA;
     constexpr int STG_BYTES = R::STG_BYTES, CTX_BYTES = R::CTX_BYTES;
@@ -350,7 +363,7 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                    b_empty = b_full + 8 * MAX_NB, acc_full = b_empty + 8 * MAX_NB, acc_empty = acc_full + 8 * MAX_REG;
 
     if (warp == EPI_WARPS + PROD_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)TMEM_COLS);
-    if (tid == THREADS - 32) {
+    if (tid == R::THREADS - 32) {
         for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, PROD_THREADS); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < MAX_NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
         for (int i = 0; i < MAX_REG; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, EPI_WARPS); }
@@ -1013,7 +1026,7 @@ inline int sm_count() {
 
 template <bool LN, class AL, class EP, int E, bool LNP = false>
 inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, const TcWeight& w, long long M, const EP& ep) {
-    using R = Roles<E, IsAttn<EP>::value>;
+    using R = RolesFor<E, EP>;
     static std::atomic<bool> configured[kMaxDevices];     // per instantiation and device
     const int dev = current_device();
     if (!configured[dev].load(std::memory_order_acquire)) {
@@ -1035,7 +1048,7 @@ inline cudaError_t launch_e(cudaStream_t st, const AL& al, const LnParams& ln, c
     static int pf_env = -2;
     if (pf_env == -2) { const char* e = getenv("ESCB_TC_PREFETCH"); pf_env = e ? atoi(e) : -1; }
     const int pf_dist = pf_env >= 0 ? pf_env : ((IsAttn<EP>::value || w.K >= 2 * w.N) ? 0 : 1);
-    tc_gemm_kernel<LN, AL, EP, E, LNP><<<(unsigned)grid, THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
+    tc_gemm_kernel<LN, AL, EP, E, LNP><<<(unsigned)grid, R::THREADS, smem, st>>>(al, ln, w, M, ep, (int)ntiles, NB, w.resident, pf_dist);
     return cudaGetLastError();
 }
 
