@@ -1516,4 +1516,13 @@ int escb_poll_error(escb_handle* h) {
 
 int64_t escb_launch_count(const escb_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
 
+int escb_tiling_info(int32_t N, int32_t K, int32_t role, int32_t* out) {
+    if (!out || N <= 0 || K <= 0 || role < 0 || role > 2) return fail(ESCB_EINVAL, "escb_tiling_info: bad argument");
+    const tc::Tiling t = tc::choose_tiling(N, K, role);
+    if (t.BN <= 0) return fail(ESCB_EINVAL, "escb_tiling_info: no tiling for N = %d, K = %d", N, K);
+    out[0] = t.BN; out[1] = t.nsub; out[2] = t.ntn; out[3] = t.nkb; out[4] = t.resident; out[5] = t.nmain; out[6] = t.corr;
+    out[7] = t.BN * t.nsub * (t.nmain + t.corr);
+    return ESCB_OK;
+}
+
 }  // extern "C"

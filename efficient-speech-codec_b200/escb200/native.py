@@ -26,7 +26,7 @@ EXPORTS = [
     "escb_workspace_bytes", "escb_encode", "escb_decode", "escb_forward", "escb_encode_host", "escb_decode_host",
     "escb_stft", "escb_istft", "escb_patch_embed", "escb_patch_deembed", "escb_swin_layer", "escb_pvq_encode",
     "escb_pvq_decode", "escb_codebook_argmin", "escb_launch_count", "escb_profile_begin", "escb_profile_end",
-    "escb_poll_error", "escb_code_histogram", "escb_pvq_stream", "escb_forward_feat",
+    "escb_poll_error", "escb_code_histogram", "escb_pvq_stream", "escb_forward_feat", "escb_tiling_info",
 ]
 ESCB_NUM_OPS = 20
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "escb_codebook_argmin": (C.c_int, [vp, i32, i32, vp, i64, vp, vp]),
         "escb_launch_count": (i64, [vp]),
         "escb_poll_error": (C.c_int, [vp]),
+        "escb_tiling_info": (C.c_int, [i32, i32, i32, C.POINTER(i32)]),
         "escb_code_histogram": (C.c_int, [vp, i32, i32, i32, i32, i32, vp, vp]),
         "escb_profile_begin": (C.c_int, [vp]),
         "escb_profile_end": (C.c_int, [vp, C.POINTER(EscbOpStat), C.POINTER(i32)]),

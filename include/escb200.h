@@ -220,6 +220,13 @@ ESCB_API int escb_profile_end(escb_handle* h, escb_op_stat* stats /* [ESCB_NUM_O
  * COMPLETED latched one since the last poll, else ESCB_OK.  escb_decode_host polls after its synchronisation. */
 ESCB_API int escb_poll_error(escb_handle* h);
 
+/* Host-only diagnostic (no device, no handle): how the tcgen05 engine would tile an nn.Linear weight [N, K] and split
+ * its accumulators (csrc/tc_gemm.cuh choose_tiling / acc_policy; DESIGN.md section 2 "accumulator split").  role: 0, 1, 2
+ * = 8 + 16, 16 + 8, 12 + 12 epilogue + producer warps.  out[8] = { BN (UMMA N), sub-tiles per output tile, n-tiles,
+ * 32-wide K blocks, weights resident in shared memory (0/1), main accumulators per sub-tile, corrections in their own
+ * accumulator (0/1), TMEM columns of one output tile }.  Returns ESCB_EINVAL for shapes the engine cannot tile. */
+ESCB_API int escb_tiling_info(int32_t N, int32_t K, int32_t role, int32_t* out);
+
 #ifdef ESCB_TC_TRACE
 /* Debug builds only (make trace): per-role cycle counters of the tcgen05 engine, 16 x 1024 u64 (tools/trace_step.py).
  * First call allocates and arms the buffer; later calls synchronise and copy it to out_host. */

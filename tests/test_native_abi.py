@@ -73,3 +73,43 @@ def test_ctor_rejects_what_the_reference_rejects():
     assert m.max_streams == 6 and m.max_bps == 9.0
     with pytest.raises(AssertionError, match="multiple of overlap"):
         m.time_patches(16000 + 160)               # W = 101
+
+
+def _tiling(N, K, role=0):
+    out = (ctypes.c_int32 * 8)()
+    rc = native.lib().escb_tiling_info(N, K, role, out)
+    assert rc == 0, (N, K, role)
+    return dict(zip(("BN", "nsub", "ntn", "nkb", "resident", "nmain", "corr", "tmem"), out))
+
+
+def test_tiling_and_accumulator_split_invariants(monkeypatch):
+    """Host logic of the tcgen05 engine (csrc/tc_gemm.cuh choose_tiling / acc_policy), no device needed: every GEMM shape
+    of the three shipped configs fits tensor memory with its accumulator split, covers all output columns, never has more
+    main accumulators than K blocks, and follows the split policy of DESIGN.md section 2."""
+    for k in ("ESCB_ACC", "ESCB_ACC_KMIN", "ESCB_TILE_SERIAL"):
+        monkeypatch.delenv(k, raising=False)
+    dims = [45, 72, 96, 144, 192, 384]
+    shapes = []
+    for C in dims:
+        shapes += [(C, C, 1), (4 * C, C, 2), (C, 4 * C, 1), (3 * C, C, 0)]             # proj, mlp1, mlp2, unfused qkv
+    shapes += [(b, 2 * a, 0) for a, b in zip(dims, dims[1:])]                          # PatchMerge: 2C -> next C
+    shapes += [(2 * a, b, 1) for a, b in zip(dims, dims[1:])]                          # PatchSplit: C -> 2 * previous C
+    for N, K, role in shapes:
+        t = _tiling(N, K, role)
+        assert t["BN"] % 16 == 0 and 16 <= t["BN"] <= 208
+        assert t["tmem"] == t["BN"] * t["nsub"] * (t["nmain"] + t["corr"]) <= 512, (N, K, t)
+        assert t["BN"] * t["nsub"] * t["ntn"] >= N, (N, K, t)
+        assert t["nkb"] == (K + 31) // 32 and 1 <= t["nmain"] <= t["nkb"]
+        assert t["corr"] == (1 if K > 96 else 0), (N, K, t)                              # corrections split off beyond K = 96
+        if K <= 96:
+            assert t["nmain"] == 1
+        if K >= 1024:
+            assert t["nmain"] >= 2, (N, K, t)                                            # long reductions alternate K blocks
+    # the round-1 engine is still selectable (A-B runs, variant tests)
+    monkeypatch.setenv("ESCB_ACC", "1,0")
+    t = _tiling(384, 1536, 1)
+    assert (t["nmain"], t["corr"]) == (1, 0)
+    monkeypatch.setenv("ESCB_ACC", "4,1")
+    t = _tiling(96, 384, 1)
+    assert t["corr"] == 1 and t["nmain"] <= 4 and t["tmem"] <= 512
+    assert native.lib().escb_tiling_info(0, 32, 0, (ctypes.c_int32 * 8)()) != 0
