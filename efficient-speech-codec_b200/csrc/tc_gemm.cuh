@@ -286,7 +286,10 @@ template <class T> struct IsAttn<T, decltype((void)T::kAttn)> { static constexpr
 
 // producer-warp override per epilogue type (see Roles)
 template <class T, class = void> struct AttnProd { static constexpr int value = 0; };
-template <class T> struct AttnProd<T, decltype((void)T::kAttn)> { static constexpr int value = T::HD == 15 ? ESCB_ATTN_PROD15 : 0; };
+#ifndef ESCB_ATTN_PROD
+#define ESCB_ATTN_PROD 0
+#endif
+template <class T> struct AttnProd<T, decltype((void)T::kAttn)> { static constexpr int value = T::HD == 15 ? ESCB_ATTN_PROD15 : ESCB_ATTN_PROD; };
 template <int E, class EP> using RolesFor = Roles<E, IsAttn<EP>::value, AttnProd<EP>::value>;
 
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart; version 1 (sm_100)
