@@ -654,6 +654,20 @@ static void pack_front(Packer& P) {
     P.put(&f.embed_w, P.w("encoder.patch_embed.proj.weight"));
     P.put(&f.embed_b, P.w("encoder.patch_embed.proj.bias"));
     P.put_ln(f.embed_ln, "encoder.patch_embed.norm", C0);
+    f.embed_k_ok = 0;
+    if (C0 == 45 && h->pf == 3 && h->pt == 2) {
+        const std::vector<float>& ew = P.w("encoder.patch_embed.proj.weight");
+        const std::vector<float>& eb = P.w("encoder.patch_embed.proj.bias");
+        const std::vector<float>& eg = P.w("encoder.patch_embed.norm.weight");
+        const std::vector<float>& ebe = P.w("encoder.patch_embed.norm.bias");
+        if (ew.size() == 45 * 12 && eb.size() == 45 && eg.size() == 45 && ebe.size() == 45) {
+            memcpy(f.embed_k.w, ew.data(), sizeof f.embed_k.w);
+            memcpy(f.embed_k.b, eb.data(), sizeof f.embed_k.b);
+            memcpy(f.embed_k.g, eg.data(), sizeof f.embed_k.g);
+            memcpy(f.embed_k.be, ebe.data(), sizeof f.embed_k.be);
+            f.embed_k_ok = 1;
+        }
+    }
     // de_proj1 (scale.py:66-68): K = tap*ldc(C0) + c
     // Output columns are padded per sub-pixel to the pixel pitch: n' = s*ldc(C0) + c for the reference's n = s*C0 + c
     // (zero weight / bias in the 3 pad channels), so the pixel-shuffle epilogue writes whole aligned float4s and every

@@ -7,11 +7,18 @@ namespace escb {
 
 static inline LnParams noln(Launcher& L) { return LnParams{nullptr, nullptr, 0.f, nullptr, L.next_trace(), nullptr, nullptr}; }
 
+#ifndef ESCB_C3_TPT
+#define ESCB_C3_TPT 1
+#endif
+constexpr int kC3Tpt = ESCB_C3_TPT;      // frames per thread of the specialised output conv (1, 2 or 4; measured in DESIGN.md)
 static size_t conv3_smem_bytes(int ld) { return (size_t)(kC3F + 2) * ((kC3T + 2) * ld + 4) * sizeof(float); }
 
 cudaError_t frontend_init() {
-    return cudaFuncSetAttribute(conv3x3_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)conv3_smem_bytes(ldc(kEmbedMaxC)));
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_out_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)conv3_smem_bytes(ldc(kEmbedMaxC)));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv3x3_out_kernel<45, kC3Tpt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv3_smem_bytes(ldc(45)));
+    return e;
 }
 
 void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long Ls, int T, float* Sf) {
@@ -23,10 +30,13 @@ void op_stft(Launcher& L, const FrontW& f, const float* audio, int B, long long 
 
 void op_patch_embed(Launcher& L, const FrontW& f, const float* Sf, int B, int T, int H, int W, float* tok, int ld) {
     const long long total = (long long)B * H * W;
-    const int threads = 128;
     L.begin(OP_EMBED, 2.0 * total * f.C0 * 2 * f.pf * f.pt, 4.0 * total * (2.0 * f.pf * f.pt + f.C0));
-    patch_embed_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, L.st>>>(
-        Sf, T, f.F, tok, ld, f.embed_w, f.embed_b, f.embed_ln.g, f.embed_ln.b, f.C0, f.pf, f.pt, H, W, total, kLnEps);
+    dim3 grid((H + kPeH - 1) / kPeH, (W + kPeW - 1) / kPeW, B);
+    if (f.embed_k_ok && ld >= 48)
+        patch_embed45_kernel<<<grid, kPeH * kPeW, 0, L.st>>>(Sf, T, f.F, tok, ld, f.embed_k, H, W, kLnEps);
+    else
+        patch_embed_kernel<<<grid, kPeH * kPeW, 0, L.st>>>(Sf, T, f.F, tok, ld, f.embed_w, f.embed_b, f.embed_ln.g, f.embed_ln.b,
+                                                          f.C0, f.pf, f.pt, H, W, kLnEps);
     L.note(cudaGetLastError());
 }
 
@@ -41,8 +51,12 @@ void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, i
     const long long total = (long long)B * Fq * T2;
     L.begin(OP_DEEMBED2, 2.0 * total * 2 * 9 * f.C0, 4.0 * total * (f.C0 + 2.0));
     dim3 grid((Fq + kC3F - 1) / kC3F, (T2 + kC3T - 1) / kC3T, B);
-    conv3x3_out_kernel<<<grid, 256, conv3_smem_bytes(ld), L.st>>>(Y1, ld, f.C0, Fq, T2, f.de2_k, f.de2_bias[0],
-                                                                 f.de2_bias[1], Xf);
+    if (f.C0 == 45)
+        conv3x3_out_kernel<45, kC3Tpt><<<grid, 32 * kC3T / kC3Tpt, conv3_smem_bytes(ld), L.st>>>(Y1, ld, f.C0, Fq, T2, f.de2_k,
+                                                                                            f.de2_bias[0], f.de2_bias[1], Xf);
+    else
+        conv3x3_out_kernel<0, 1><<<grid, 32 * kC3T, conv3_smem_bytes(ld), L.st>>>(Y1, ld, f.C0, Fq, T2, f.de2_k, f.de2_bias[0],
+                                                                                f.de2_bias[1], Xf);
     L.note(cudaGetLastError());
 }
 

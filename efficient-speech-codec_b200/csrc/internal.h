@@ -60,6 +60,8 @@ struct RvqW {
 };
 
 struct Conv3Weights { float w[9 * 64 * 2]; };        // [tap][c][2], c < kEmbedMaxC
+// patch-embedding parameters of the shipped geometry (C0 = 45, 3 x 2 patches of 2 planes) as a by-value kernel parameter
+struct EmbedWeights { float w[45 * 12]; float b[45], g[45], be[45]; };
 
 struct FrontW {
     int F, win, hop, nov, C0, pf, pt;
@@ -67,6 +69,8 @@ struct FrontW {
     GemmWeight idft;                                 // [nov*2F][hop] windowed inverse basis
     const float* wsq;                                // [win] squared synthesis window
     const float* embed_w; const float* embed_b; LnW embed_ln;
+    EmbedWeights embed_k;                            // the same values for patch_embed45_kernel (valid when embed_k_ok)
+    int embed_k_ok;
     GemmWeight de1;                                  // conv5x5 as implicit GEMM, K = 25*ldc(C0)
     const float* de2_w; const float* de2_b;          // [9][C0][2], [2]
     float de2_bias[2];

@@ -261,54 +261,130 @@ codebook_argmin_kernel(const float* __restrict__ z, const int ldz, const int d_s
 // PatchEmbed.forward (scale.py:42-50): non-overlapping (pf x pt) patches of the 2-plane spectrum -> C0 channels,
 // then LayerNorm(C0).  The spectrum is read frame-major [B, T, 2F]; one thread per token, adjacent threads take
 // adjacent frequency patches so the pf-float reads coalesce.  Weight k index = (c*pf + s1)*pt + s2.
-static __global__ void patch_embed_kernel(const float* __restrict__ Sf, const int T, const int F, float* __restrict__ tok,
-                                   const int ld, const float* __restrict__ w, const float* __restrict__ bias,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, const int C0,
-                                   const int pf, const int pt, const int H, const int W, const long long total,
-                                   const float eps) {
+constexpr int kPeH = 32, kPeW = 4;       // tokens per block: 32 frequency patches x 4 time patches
+static __global__ void __launch_bounds__(kPeH * kPeW)
+patch_embed_kernel(const float* __restrict__ Sf, const int T, const int F, float* __restrict__ tok,
+                   const int ld, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const int C0,
+                   const int pf, const int pt, const int H, const int W, const float eps) {
+    // One thread per token: lanes run along the frequency axis, so the pf-float reads of a warp cover one contiguous
+    // stretch of the frame; the finished rows go through shared memory ([w][h] rows of pitch 49: conflict-free scalar
+    // writes) and leave as float4 segments - the kPeW tokens of one frequency row are kPeW * ld contiguous floats of the
+    // token map (l = h * W + w).  Writing each row from its own thread (45 scalar stores, W * ld floats between
+    // neighbouring lanes) cost 307 us per step for 145 MB.
     __shared__ float sw[kEmbedMaxC * kEmbedMaxK];
     __shared__ float sb[kEmbedMaxC], sg[kEmbedMaxC], sbe[kEmbedMaxC];
-    const int KP = 2 * pf * pt;
-    for (int i = threadIdx.x; i < C0 * KP; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < C0; i += blockDim.x) { sb[i] = bias[i]; sg[i] = gamma[i]; sbe[i] = beta[i]; }
+    constexpr int PITCH = kEmbedMaxC + 1 > 49 ? kEmbedMaxC + 1 : 49;
+    __shared__ float rows[kPeH * kPeW * PITCH];
+    const int KP = 2 * pf * pt, tid = threadIdx.x;
+    for (int i = tid; i < C0 * KP; i += kPeH * kPeW) sw[i] = w[i];
+    for (int i = tid; i < C0; i += kPeH * kPeW) { sb[i] = bias[i]; sg[i] = gamma[i]; sbe[i] = beta[i]; }
     __syncthreads();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int h = (int)(idx % H);
-    const int wq = (int)((idx / H) % W);
-    const long long b = idx / ((long long)H * W);
-    float in[kEmbedMaxK];
+    const int hl = tid & (kPeH - 1), wl = tid / kPeH;
+    const int h = blockIdx.x * kPeH + hl, wq = blockIdx.y * kPeW + wl;
+    const long long b = blockIdx.z;
+    if (h < H && wq < W) {
+        float in[kEmbedMaxK];
 #pragma unroll
-    for (int k = 0; k < kEmbedMaxK; ++k) {
-        if (k < KP) {
-            const int c = k / (pf * pt), rem = k - c * pf * pt;
-            const int s1 = rem / pt, s2 = rem - s1 * pt;
-            in[k] = __ldg(Sf + (b * T + (long long)wq * pt + s2) * (2 * F) + c * F + h * pf + s1);
-        } else in[k] = 0.f;
+        for (int k = 0; k < kEmbedMaxK; ++k) {
+            if (k < KP) {
+                const int c = k / (pf * pt), rem = k - c * pf * pt;
+                const int s1 = rem / pt, s2 = rem - s1 * pt;
+                in[k] = __ldg(Sf + (b * T + (long long)wq * pt + s2) * (2 * F) + c * F + h * pf + s1);
+            } else in[k] = 0.f;
+        }
+        float y[kEmbedMaxC];
+        float s = 0.f;
+#pragma unroll
+        for (int n = 0; n < kEmbedMaxC; ++n) {
+            if (n < C0) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < kEmbedMaxK; ++k)
+                    if (k < KP) acc = fmaf(in[k], sw[n * KP + k], acc);
+                y[n] = acc + sb[n];
+                s += y[n];
+            }
+        }
+        const float mean = s / (float)C0;
+        float q = 0.f;
+#pragma unroll
+        for (int n = 0; n < kEmbedMaxC; ++n)
+            if (n < C0) { const float dlt = y[n] - mean; q = fmaf(dlt, dlt, q); }
+        const float rstd = 1.0f / sqrtf(q / (float)C0 + eps);
+        float* r = rows + (wl * kPeH + hl) * PITCH;
+#pragma unroll
+        for (int n = 0; n < kEmbedMaxC; ++n)
+            if (n < C0) r[n] = (y[n] - mean) * rstd * sg[n] + sbe[n];
     }
-    float y[kEmbedMaxC];
-    float s = 0.f;
+    __syncthreads();
+    // float4 j of the block's output: frequency row j / (kPeW * ld4), then the kPeW tokens of that row back to back
+    const int ld4 = ld >> 2, per_h = kPeW * ld4;
+    for (int j = tid; j < kPeH * per_h; j += kPeH * kPeW) {
+        const int hh = j / per_h, rem = j - hh * per_h, ww = rem / ld4, c4 = rem - ww * ld4;
+        const int hg = blockIdx.x * kPeH + hh, wg = blockIdx.y * kPeW + ww;
+        if (hg >= H || wg >= W) continue;
+        const float* r = rows + (ww * kPeH + hh) * PITCH + 4 * c4;
+        float4 v;
+        v.x = 4 * c4 + 0 < C0 ? r[0] : 0.f;
+        v.y = 4 * c4 + 1 < C0 ? r[1] : 0.f;
+        v.z = 4 * c4 + 2 < C0 ? r[2] : 0.f;
+        v.w = 4 * c4 + 3 < C0 ? r[3] : 0.f;
+        *reinterpret_cast<float4*>(tok + ((b * H + hg) * (long long)W + wg) * ld + 4 * c4) = v;
+    }
+}
+
+// The shipped geometry (C0 = 45, pf x pt = 3 x 2, 2 planes) with every index a compile-time constant: the 540 weights,
+// the bias and the LayerNorm vectors come straight from the constant bank (kernel parameter), no shared-memory operand
+// per multiply-add.  Same arithmetic and order as patch_embed_kernel.
+static __global__ void __launch_bounds__(kPeH * kPeW)
+patch_embed45_kernel(const float* __restrict__ Sf, const int T, const int F, float* __restrict__ tok, const int ld,
+                     const __grid_constant__ EmbedWeights ew, const int H, const int W, const float eps) {
+    constexpr int C0 = 45, PF = 3, PT = 2, KP = 2 * PF * PT, PITCH = 49;
+    __shared__ float rows[kPeH * kPeW * PITCH];
+    const int tid = threadIdx.x, hl = tid & (kPeH - 1), wl = tid / kPeH;
+    const int h = blockIdx.x * kPeH + hl, wq = blockIdx.y * kPeW + wl;
+    const long long b = blockIdx.z;
+    if (h < H && wq < W) {
+        float in[KP];
 #pragma unroll
-    for (int n = 0; n < kEmbedMaxC; ++n) {
-        if (n < C0) {
+        for (int k = 0; k < KP; ++k) {
+            const int c = k / (PF * PT), rem = k - c * PF * PT, s1 = rem / PT, s2 = rem - s1 * PT;
+            in[k] = __ldg(Sf + (b * T + (long long)wq * PT + s2) * (2 * F) + c * F + h * PF + s1);
+        }
+        float y[C0];
+        float s = 0.f;
+#pragma unroll
+        for (int n = 0; n < C0; ++n) {
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < kEmbedMaxK; ++k)
-                if (k < KP) acc = fmaf(in[k], sw[n * KP + k], acc);
-            y[n] = acc + sb[n];
+            for (int k = 0; k < KP; ++k) acc = fmaf(in[k], ew.w[n * KP + k], acc);
+            y[n] = acc + ew.b[n];
             s += y[n];
         }
+        const float mean = s / (float)C0;
+        float q = 0.f;
+#pragma unroll
+        for (int n = 0; n < C0; ++n) { const float dlt = y[n] - mean; q = fmaf(dlt, dlt, q); }
+        const float rstd = 1.0f / sqrtf(q / (float)C0 + eps);
+        float* r = rows + (wl * kPeH + hl) * PITCH;
+#pragma unroll
+        for (int n = 0; n < C0; ++n) r[n] = (y[n] - mean) * rstd * ew.g[n] + ew.be[n];
     }
-    const float mean = s / (float)C0;
-    float q = 0.f;
-#pragma unroll
-    for (int n = 0; n < kEmbedMaxC; ++n)
-        if (n < C0) { const float dlt = y[n] - mean; q = fmaf(dlt, dlt, q); }
-    const float rstd = 1.0f / sqrtf(q / (float)C0 + eps);
-    float* o = tok + (b * H * W + (long long)h * W + wq) * ld;
-#pragma unroll
-    for (int n = 0; n < kEmbedMaxC; ++n)
-        if (n < C0) o[n] = (y[n] - mean) * rstd * sg[n] + sbe[n];
+    __syncthreads();
+    const int ld4 = ld >> 2, per_h = kPeW * ld4;
+    for (int j = tid; j < kPeH * per_h; j += kPeH * kPeW) {
+        const int hh = j / per_h, rem = j - hh * per_h, ww = rem / ld4, c4 = rem - ww * ld4;
+        const int hg = blockIdx.x * kPeH + hh, wg = blockIdx.y * kPeW + ww;
+        if (hg >= H || wg >= W) continue;
+        const float* r = rows + (ww * kPeH + hh) * PITCH + 4 * c4;
+        float4 v;
+        v.x = 4 * c4 + 0 < C0 ? r[0] : 0.f;
+        v.y = 4 * c4 + 1 < C0 ? r[1] : 0.f;
+        v.z = 4 * c4 + 2 < C0 ? r[2] : 0.f;
+        v.w = 4 * c4 + 3 < C0 ? r[3] : 0.f;
+        *reinterpret_cast<float4*>(tok + ((b * H + hg) * (long long)W + wg) * ld + 4 * c4) = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ output conv
@@ -318,16 +394,25 @@ static __global__ void patch_embed_kernel(const float* __restrict__ Sf, const in
 // loads (row pitch padded by 4 floats so the 32 lanes of a warp, one bin each, read conflict-free), the taps
 // [tap][c][2] arrive as a by-value kernel parameter so every FMA takes its weight from the constant bank, and
 // lanes run along the bin axis so both output planes are written as 128-byte segments.
+// C0T > 0: the channel count as a compile-time constant (45 in every shipped config).  Every tap index is then an
+// immediate, so each FMA takes its weight straight from the constant bank; with a run-time C0 the compiler fetched the
+// weights with 870 uniform constant loads per thread in front of the 1 548 FMAs (0.63 ms per step -> see DESIGN.md).
 constexpr int kC3F = 32, kC3T = 8;
-static __global__ void __launch_bounds__(256)
-conv3x3_out_kernel(const float* __restrict__ Y1, const int LD, const int C0, const int F, const int T2,
+// TPT consecutive frames per thread: a staged pixel feeds every output whose 3-wide window covers it, so the shared
+// memory reads per output drop from 108 to 36 (TPT + 2) / TPT float4 and the 2 TPT accumulators are independent FMA
+// chains.  Every output still accumulates in the order (kh, kw, c): the results do not depend on TPT.
+template <int C0T, int TPT>
+static __global__ void __launch_bounds__(32 * kC3T / TPT)
+conv3x3_out_kernel(const float* __restrict__ Y1, const int LD, const int C0r, const int F, const int T2,
                    const __grid_constant__ Conv3Weights wk, const float b0, const float b1, float* __restrict__ Xf) {
+    constexpr int NT = 32 * kC3T / TPT;
+    const int C0 = C0T > 0 ? C0T : C0r;
     const int PITCH = (kC3T + 2) * LD + 4;
     extern __shared__ __align__(16) float halo[];          // [kC3F + 2][PITCH]
     const int f0 = blockIdx.x * kC3F, t0 = blockIdx.y * kC3T;
     const long long b = blockIdx.z;
     const int ROW4 = (kC3T + 2) * LD / 4;
-    for (int i = threadIdx.x; i < (kC3F + 2) * ROW4; i += 256) {
+    for (int i = threadIdx.x; i < (kC3F + 2) * ROW4; i += NT) {
         const int fr = i / ROW4, j = i - fr * ROW4;
         const int tt = j / (LD / 4), c4 = j - tt * (LD / 4);
         const int f = f0 + fr - 1, t = t0 + tt - 1;
@@ -337,32 +422,51 @@ conv3x3_out_kernel(const float* __restrict__ Y1, const int LD, const int C0, con
         *reinterpret_cast<float4*>(halo + fr * PITCH + tt * LD + c4 * 4) = v;
     }
     __syncthreads();
-    const int fl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-    const int f = f0 + fl, t = t0 + tl;
-    float a0 = 0.f, a1 = 0.f;
+    const int fl = threadIdx.x & 31, tl = (threadIdx.x >> 5) * TPT;
+    const int f = f0 + fl;
+    float a0[TPT], a1[TPT];
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const float* p = halo + (fl + kh) * PITCH + (tl + kw) * LD;
-            const float* wv = wk.w + (kh * 3 + kw) * C0 * 2;
-#pragma unroll 4
+        for (int col = 0; col < TPT + 2; ++col) {
+            const float* p = halo + (fl + kh) * PITCH + (tl + col) * LD;
+#pragma unroll (C0T > 0 ? 16 : 4)
             for (int c = 0; c + 3 < C0; c += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(p + c);
-                a0 = fmaf(v.x, wv[2 * c + 0], a0); a1 = fmaf(v.x, wv[2 * c + 1], a1);
-                a0 = fmaf(v.y, wv[2 * c + 2], a0); a1 = fmaf(v.y, wv[2 * c + 3], a1);
-                a0 = fmaf(v.z, wv[2 * c + 4], a0); a1 = fmaf(v.z, wv[2 * c + 5], a1);
-                a0 = fmaf(v.w, wv[2 * c + 6], a0); a1 = fmaf(v.w, wv[2 * c + 7], a1);
+#pragma unroll
+                for (int j = 0; j < TPT; ++j) {
+                    const int kw = col - j;                // output j sees this pixel through tap kw
+                    if (kw < 0 || kw > 2) continue;
+                    const float* wv = wk.w + (kh * 3 + kw) * C0 * 2;
+                    a0[j] = fmaf(v.x, wv[2 * c + 0], a0[j]); a1[j] = fmaf(v.x, wv[2 * c + 1], a1[j]);
+                    a0[j] = fmaf(v.y, wv[2 * c + 2], a0[j]); a1[j] = fmaf(v.y, wv[2 * c + 3], a1[j]);
+                    a0[j] = fmaf(v.z, wv[2 * c + 4], a0[j]); a1[j] = fmaf(v.z, wv[2 * c + 5], a1[j]);
+                    a0[j] = fmaf(v.w, wv[2 * c + 6], a0[j]); a1[j] = fmaf(v.w, wv[2 * c + 7], a1[j]);
+                }
             }
+#pragma unroll
             for (int c = C0 & ~3; c < C0; ++c) {
                 const float v = p[c];
-                a0 = fmaf(v, wv[2 * c], a0); a1 = fmaf(v, wv[2 * c + 1], a1);
+#pragma unroll
+                for (int j = 0; j < TPT; ++j) {
+                    const int kw = col - j;
+                    if (kw < 0 || kw > 2) continue;
+                    const float* wv = wk.w + (kh * 3 + kw) * C0 * 2;
+                    a0[j] = fmaf(v, wv[2 * c], a0[j]); a1[j] = fmaf(v, wv[2 * c + 1], a1[j]);
+                }
             }
         }
-    if (f < F && t < T2) {
-        float* o = Xf + (b * T2 + t) * (long long)(2 * F);
-        o[f] = a0 + b0;
-        o[F + f] = a1 + b1;
+    if (f < F) {
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+            const int t = t0 + tl + j;
+            if (t >= T2) continue;
+            float* o = Xf + (b * T2 + t) * (long long)(2 * F);
+            o[f] = a0[j] + b0;
+            o[F + f] = a1[j] + b1;
+        }
     }
 }
 
