@@ -337,14 +337,16 @@ patch_embed_kernel(const float* __restrict__ Sf, const int T, const int F, float
 // The shipped geometry (C0 = 45, pf x pt = 3 x 2, 2 planes) with every index a compile-time constant: the 540 weights,
 // the bias and the LayerNorm vectors come straight from the constant bank (kernel parameter), no shared-memory operand
 // per multiply-add.  Same arithmetic and order as patch_embed_kernel.
-static __global__ void __launch_bounds__(kPeH * kPeW)
+static __global__ void __launch_bounds__(kPeH * kPeW, 6)
 patch_embed45_kernel(const float* __restrict__ Sf, const int T, const int F, float* __restrict__ tok, const int ld,
                      const __grid_constant__ EmbedWeights ew, const int H, const int W, const float eps) {
     constexpr int C0 = 45, PF = 3, PT = 2, KP = 2 * PF * PT, PITCH = 49;
-    __shared__ float rows[kPeH * kPeW * PITCH];
+    __shared__ float rows[kPeH * kPeW * PITCH];            // per token: 45 conv outputs, then its mean and rstd
+    __shared__ float sg[48], sbe[48];
     const int tid = threadIdx.x, hl = tid & (kPeH - 1), wl = tid / kPeH;
     const int h = blockIdx.x * kPeH + hl, wq = blockIdx.y * kPeW + wl;
     const long long b = blockIdx.z;
+    if (tid < 48) { sg[tid] = tid < C0 ? ew.g[tid] : 0.f; sbe[tid] = tid < C0 ? ew.be[tid] : 0.f; }
     if (h < H && wq < W) {
         float in[KP];
 #pragma unroll
@@ -352,24 +354,25 @@ patch_embed45_kernel(const float* __restrict__ Sf, const int T, const int F, flo
             const int c = k / (PF * PT), rem = k - c * PF * PT, s1 = rem / PT, s2 = rem - s1 * PT;
             in[k] = __ldg(Sf + (b * T + (long long)wq * PT + s2) * (2 * F) + c * F + h * PF + s1);
         }
-        float y[C0];
+        // the outputs go to the token's shared-memory row as they are produced (keeping all 45 in registers next to the
+        // 540 constant-bank weights made ptxas preload weights: 255 registers or 900 bytes of spills)
+        float* r = rows + (wl * kPeH + hl) * PITCH;
         float s = 0.f;
-#pragma unroll
+#pragma unroll 5                                            // full unrolling interleaves all 45 chains: 257 spilled registers
         for (int n = 0; n < C0; ++n) {
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < KP; ++k) acc = fmaf(in[k], ew.w[n * KP + k], acc);
-            y[n] = acc + ew.b[n];
-            s += y[n];
+            const float y = acc + ew.b[n];
+            r[n] = y;
+            s += y;
         }
         const float mean = s / (float)C0;
         float q = 0.f;
-#pragma unroll
-        for (int n = 0; n < C0; ++n) { const float dlt = y[n] - mean; q = fmaf(dlt, dlt, q); }
-        const float rstd = 1.0f / sqrtf(q / (float)C0 + eps);
-        float* r = rows + (wl * kPeH + hl) * PITCH;
-#pragma unroll
-        for (int n = 0; n < C0; ++n) r[n] = (y[n] - mean) * rstd * ew.g[n] + ew.be[n];
+#pragma unroll 5
+        for (int n = 0; n < C0; ++n) { const float dlt = r[n] - mean; q = fmaf(dlt, dlt, q); }
+        r[C0] = mean;
+        r[C0 + 1] = 1.0f / sqrtf(q / (float)C0 + eps);
     }
     __syncthreads();
     const int ld4 = ld >> 2, per_h = kPeW * ld4;
@@ -377,13 +380,15 @@ patch_embed45_kernel(const float* __restrict__ Sf, const int T, const int F, flo
         const int hh = j / per_h, rem = j - hh * per_h, ww = rem / ld4, c4 = rem - ww * ld4;
         const int hg = blockIdx.x * kPeH + hh, wg = blockIdx.y * kPeW + ww;
         if (hg >= H || wg >= W) continue;
-        const float* r = rows + (ww * kPeH + hh) * PITCH + 4 * c4;
+        const float* r = rows + (ww * kPeH + hh) * PITCH;
+        const float mean = r[C0], rstd = r[C0 + 1];
+        const int c = 4 * c4;
         float4 v;
-        v.x = 4 * c4 + 0 < C0 ? r[0] : 0.f;
-        v.y = 4 * c4 + 1 < C0 ? r[1] : 0.f;
-        v.z = 4 * c4 + 2 < C0 ? r[2] : 0.f;
-        v.w = 4 * c4 + 3 < C0 ? r[3] : 0.f;
-        *reinterpret_cast<float4*>(tok + ((b * H + hg) * (long long)W + wg) * ld + 4 * c4) = v;
+        v.x = c + 0 < C0 ? (r[c + 0] - mean) * rstd * sg[c + 0] + sbe[c + 0] : 0.f;
+        v.y = c + 1 < C0 ? (r[c + 1] - mean) * rstd * sg[c + 1] + sbe[c + 1] : 0.f;
+        v.z = c + 2 < C0 ? (r[c + 2] - mean) * rstd * sg[c + 2] + sbe[c + 2] : 0.f;
+        v.w = c + 3 < C0 ? (r[c + 3] - mean) * rstd * sg[c + 3] + sbe[c + 3] : 0.f;
+        *reinterpret_cast<float4*>(tok + ((b * H + hg) * (long long)W + wg) * ld + c) = v;
     }
 }
 
