@@ -51,7 +51,9 @@ void op_deembed(Launcher& L, const FrontW& f, const float* tok, int ld, int B, i
     const long long total = (long long)B * Fq * T2;
     L.begin(OP_DEEMBED2, 2.0 * total * 2 * 9 * f.C0, 4.0 * total * (f.C0 + 2.0));
     dim3 grid((Fq + kC3F - 1) / kC3F, (T2 + kC3T - 1) / kC3T, B);
-    if (f.C0 == 45)
+    if (f.C0 == 45 && ld == 48 && !getenv("ESCB_C3_WHOLE"))
+        conv3x3_out45_kernel<<<grid, 256, 0, L.st>>>(Y1, Fq, T2, f.de2_k, f.de2_bias[0], f.de2_bias[1], Xf);
+    else if (f.C0 == 45)
         conv3x3_out_kernel<45, kC3Tpt><<<grid, 32 * kC3T / kC3Tpt, conv3_smem_bytes(ld), L.st>>>(Y1, ld, f.C0, Fq, T2, f.de2_k,
                                                                                             f.de2_bias[0], f.de2_bias[1], Xf);
     else
