@@ -621,7 +621,7 @@ def main_b200(args):
         roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                 "peak_source": peaks["src"] + " MEASURED_PEAKS.json hbm copy"}
     traffic, traffic_src = None, None
-    for tf in ("r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
+    for tf in ("r2d_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         try:                                 # measured DRAM bytes per launch of that class (tools/ncu_traffic.py over one step)
             tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
             if args.config == "base" and B == 36 and top in tj["classes"]:

@@ -32,10 +32,10 @@ RULES = [   # (substring of the demangled kernel name, class); first match wins
     ("ACodes", "pvq_up_gemm"),
     ("codebook_argmin_kernel", "codebook_argmin"),
     ("AIm2col", "deembed_conv5x5_gemm"),
-    ("conv3x3_out_kernel", "deembed_conv3x3"),
+    ("conv3x3_out", "deembed_conv3x3"),
     ("AStftFrames", "stft_gemm"),
     ("AIstft", "istft_gemm"),
-    ("patch_embed_kernel", "patch_embed"),
+    ("patch_embed", "patch_embed"),
     ("vq_loss_kernel", "vq_loss"),
     ("transpose_kernel", "layout"),
     ("repitch_kernel", "layout"),
