@@ -335,6 +335,28 @@ def test_deep_layer_error_is_fp32_grade(base0):
     assert float((y - ref).abs().max() / ref.abs().max()) <= 2.5e-6
 
 
+def test_generic_frontend_kernels_other_first_width(monkeypatch):
+    """h_dims[0] = 48 (no shipped config): the patch embedding and the 3x3 output conv run their generic kernels (the
+    shipped width 45 has constant-bank specialisations), the first level takes the unfused MLP pair (no fused plan for
+    C = 48).  Codes bit-exact and audio within tolerance against the oracle; and the whole-halo output conv
+    (ESCB_C3_WHOLE=1) equals the channel-staged one for the shipped width up to summation order."""
+    cfg = dict(BASE, h_dims=[48, 72, 96, 144, 192, 384])
+    m, _ = make_native(cfg, 3)
+    o = make_oracle(cfg, 3)[0]
+    x = synth_audio(2, 16000 + 80 * 4 * 5, seed=12)
+    codes, fs = m.encode(x.cuda(), 6)
+    co, fo = o.encode(x, 6)
+    assert tuple(fs) == tuple(fo) and torch.equal(codes.cpu(), co)
+    assert maxabs(m.decode(codes, fs).cpu(), o.decode(co, fs)) <= AUDIO_TOL
+    base = make_native(BASE, 0)[0]
+    cb, fb = base.encode(x.cuda(), 6)
+    a0 = base.decode(cb, fb)
+    monkeypatch.setenv("ESCB_C3_WHOLE", "1")                  # read per launch
+    a1 = base.decode(cb, fb)
+    monkeypatch.delenv("ESCB_C3_WHOLE")
+    assert maxabs(a0.cpu(), a1.cpu()) <= 2e-6
+
+
 @pytest.mark.parametrize("alt", ["", "0", "1"])
 def test_large_b64_config3(alt, monkeypatch):
     """BASELINE configs[2]: ESC-Large at batch 64.  tc::pick switches weight tilings with the row count, so the B=64
