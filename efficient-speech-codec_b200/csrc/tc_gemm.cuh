@@ -596,21 +596,33 @@ tc_gemm_kernel(const AL al, const LnParams ln, const TcWeight w, const long long
                 }
             }
             for (int sub = 0; sub < nsub; ++sub) {
-                { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
-                tc_fence_after();
-                const uint32_t tbase = tmem + reg * RW + ((uint32_t)(q * 32) << 16);
-                for (int ch = part; ch < nch; ch += E) {
-                    // bias and residual of this lane's four row segments are requested before the accumulator is
-                    // read, so their latency (L2 hits: the rows were prefetched a tile ahead) overlaps the staging
+                // bias and residual of this lane's four row segments are requested before the accumulator is read, so
+                // their latency (L2 hits: the rows were prefetched a tile ahead) overlaps the staging - and for the
+                // warp's FIRST chunk of a sub-tile before the wait for the accumulator itself (ESCB_EPI_NOPRE: after it)
+                float4 b4 = zero4(), res[4], cs4 = zero4(), bw4 = zero4();
+                auto request = [&](int ch) {
                     const int n = n0 + sub * BN + ch * 16 + c4 * 4;
-                    const bool full4 = n + 3 < N;
-                    float4 b4 = zero4(), res[4], cs4 = zero4(), bw4 = zero4();
-                    if (full4) {
+                    if (n + 3 < N) {
                         if constexpr (LNP) { cs4 = ldg4(ln.cs + n); bw4 = ldg4(ln.bw + n); }
                         b4 = ep.bias4(n);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) res[i] = ((okm >> i) & 1u) ? ep.resid4(cr[i], n) : zero4();
                     }
+                };
+#ifndef ESCB_EPI_NOPRE
+                if (part < nch) request(part);
+#endif
+                { TC_T0(t_); mbar_wait(acc_full + 8 * reg, rphase); TC_ACC(0, t_); }
+                tc_fence_after();
+                const uint32_t tbase = tmem + reg * RW + ((uint32_t)(q * 32) << 16);
+                for (int ch = part; ch < nch; ch += E) {
+                    const int n = n0 + sub * BN + ch * 16 + c4 * 4;
+                    const bool full4 = n + 3 < N;
+#ifndef ESCB_EPI_NOPRE
+                    if (ch != part) request(ch);
+#else
+                    request(ch);
+#endif
                     float v[16];
                     tmem_ld_acc<16>(tbase + (uint32_t)(ch * 16), v, accs, BN);
                     tmem_ld_wait<16>(v);
