@@ -24,8 +24,10 @@
 // the tensor pipe works on G1 of the next chunks while the GELU warps convert the current one.
 //
 // TMEM columns (512): A1 images 2 * Kp16 per buffer | R0, R1 (64 each) | L0[, L1] (64 each) | ACC2 (N2 per buffer) [| ACC2 corrections].
-// Precision: identical to the unfused tcgen05 path (same 3xTF32 split, same k order, same bias / GELU / residual
-// arithmetic); only the LayerNorm sums are accumulated per thread instead of by 8 lanes.
+// Precision: the arithmetic of the unfused tcgen05 path (same 3xTF32 split, same k order, same bias / GELU / residual
+// formulas); the LayerNorm sums are accumulated per thread instead of by 8 lanes, and fc2's partial products go to ONE
+// main accumulator (+ one for the corrections at C = 45 / 72) where the unfused mlp2 may alternate K blocks between two
+// mains: the two paths agree to fp32 rounding, not bit for bit (tests/test_gpu_parity.py::test_engine_variants_agree).
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>

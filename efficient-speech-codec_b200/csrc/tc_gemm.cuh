@@ -6,7 +6,9 @@
 // 3..742 of 3600 codes per stream (hard part 1).  Every operand x is split into
 // hi = tf32(x), lo = tf32(x - hi); D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi in the fp32 TMEM accumulator
 // (the dropped lo*lo term is 2^-22 relative).  Weights are split once at escb_finalize(); activations are split
-// by the A-producer warps after the fused gather / LayerNorm.
+// by the A-producer warps after the fused gather / LayerNorm.  The tensor core TRUNCATES its accumulator (~0.6 ulp of
+// bias per MMA), so the hi*hi products and the corrections of long reductions go to separate TMEM accumulators that the
+// epilogue adds in fp32 ("accumulator split": acc_policy below, TcWeight::nmain / corr).
 //
 // One persistent CTA per SM (832 threads), warp-specialised, looping over 128 x NT output tiles (NT <= 512).
 // 24 of the 26 warps are shared between the epilogue and the A producers in one of three splits (struct Roles:
