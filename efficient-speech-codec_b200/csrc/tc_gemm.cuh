@@ -291,7 +291,13 @@ template <class T, class = void> struct AttnProd { static constexpr int value = 
 #ifndef ESCB_ATTN_PROD
 #define ESCB_ATTN_PROD 0
 #endif
-template <class T> struct AttnProd<T, decltype((void)T::kAttn)> { static constexpr int value = T::HD == 15 ? ESCB_ATTN_PROD15 : ESCB_ATTN_PROD; };
+#ifndef ESCB_ATTN_PROD72
+#define ESCB_ATTN_PROD72 8
+#endif
+// head widths 12 and 24 are the C = 72 levels (12 also the decoder's C = 144 level, which measured neutral): 239 -> 228 us
+template <class T> struct AttnProd<T, decltype((void)T::kAttn)> {
+    static constexpr int value = T::HD == 15 ? ESCB_ATTN_PROD15 : ((T::HD == 12 || T::HD == 24) ? ESCB_ATTN_PROD72 : ESCB_ATTN_PROD);
+};
 template <int E, class EP> using RolesFor = Roles<E, IsAttn<EP>::value, AttnProd<EP>::value>;
 
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart; version 1 (sm_100)
